@@ -1,0 +1,207 @@
+"""ctypes binding of the C-ABI in include/atrip_b200.h (one Engine == one atrip_b200_ctx).
+
+Mirrors the header one to one; every failure of the library raises EngineError carrying
+atrip_b200_last_error().  Nothing here computes: if libatrip_b200.so is missing, loading raises.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+
+# symbols declared in include/atrip_b200.h (tests check the library exports every one)
+SYMBOLS = [
+    "atrip_b200_create", "atrip_b200_destroy", "atrip_b200_last_error", "atrip_b200_version",
+    "atrip_b200_set_epsilon", "atrip_b200_set_Tai", "atrip_b200_load_Tabij", "atrip_b200_load_Vabij",
+    "atrip_b200_load_Vijka", "atrip_b200_load_Vabci", "atrip_b200_load_Jijka", "atrip_b200_load_Jabci",
+    "atrip_b200_fill_synthetic", "atrip_b200_build_tuples", "atrip_b200_set_tuples",
+    "atrip_b200_num_tuples", "atrip_b200_get_tuples", "atrip_b200_run", "atrip_b200_tuple_debug",
+    "atrip_b200_read_slice", "atrip_b200_last_timing", "atrip_b200_kp", "atrip_b200_flops_per_tuple",
+]
+
+NAIVE, GROUP_AND_SORT = 0, 1
+TA, VIJKA, VABCI, TABIJ, VABIJ = 100, 101, 200, 201, 202
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+class Config(C.Structure):
+    _fields_ = [("device", C.c_int32), ("rank", C.c_int32), ("nranks", C.c_int32), ("with_J", C.c_int32),
+                ("No", C.c_int64), ("Nv", C.c_int64), ("batch_tuples", C.c_int64),
+                ("resident", C.c_int32), ("reserved", C.c_int32)]
+
+
+def lib_path():
+    return os.path.join(CSRC, "libatrip_b200.so")
+
+
+def build_library(force=False, verbose=False):
+    """nvcc -gencode arch=compute_100a,code=sm_100a (cross-compiles without a GPU)"""
+    cmd = ["make", "-C", CSRC] + (["-B"] if force else []) + ([] if verbose else ["-s"])
+    subprocess.check_call(cmd)
+    return lib_path()
+
+
+_dp = C.POINTER(C.c_double)
+_up = C.POINTER(C.c_uint64)
+_lib = None
+
+
+def load_library():
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.exists(path):
+        raise EngineError(f"{path} is missing: run `make -C atrip_b200/csrc` (or __graft_entry__.build()); "
+                          "there is no CPU fallback")
+    L = C.CDLL(path)
+    ctx = C.c_void_p
+    L.atrip_b200_create.argtypes = [C.POINTER(ctx), C.POINTER(Config)]
+    L.atrip_b200_destroy.argtypes = [ctx]
+    L.atrip_b200_last_error.restype = C.c_char_p
+    L.atrip_b200_version.restype = C.c_char_p
+    L.atrip_b200_set_epsilon.argtypes = [ctx, _dp, _dp]
+    for n in ("set_Tai", "load_Tabij", "load_Vabij", "load_Vijka", "load_Vabci", "load_Jijka", "load_Jabci"):
+        getattr(L, "atrip_b200_" + n).argtypes = [ctx, _dp]
+    L.atrip_b200_fill_synthetic.argtypes = [ctx, C.c_uint64, C.c_double]
+    L.atrip_b200_build_tuples.argtypes = [ctx, C.c_int32]
+    L.atrip_b200_set_tuples.argtypes = [ctx, _up, C.c_int64]
+    L.atrip_b200_num_tuples.argtypes = [ctx]
+    L.atrip_b200_num_tuples.restype = C.c_int64
+    L.atrip_b200_get_tuples.argtypes = [ctx, _up, C.c_int64]
+    L.atrip_b200_run.argtypes = [ctx, C.c_int64, C.c_int64, _dp, _dp]
+    L.atrip_b200_tuple_debug.argtypes = [ctx, C.c_int64, C.c_int64, C.c_int64, _dp, _dp, _dp]
+    L.atrip_b200_read_slice.argtypes = [ctx, C.c_int32, C.c_int64, C.c_int64, _dp]
+    L.atrip_b200_last_timing.argtypes = [ctx, _dp]
+    L.atrip_b200_kp.argtypes = [ctx]
+    L.atrip_b200_kp.restype = C.c_int64
+    L.atrip_b200_flops_per_tuple.argtypes = [ctx]
+    L.atrip_b200_flops_per_tuple.restype = C.c_double
+    _lib = L
+    return L
+
+
+def _ptr(a):
+    """double* of a host buffer: numpy float64 array, or an int address (e.g. pinned torch storage)"""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return C.cast(a, _dp)
+    assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"] or a.flags["F_CONTIGUOUS"]
+    return a.ctypes.data_as(_dp)
+
+
+class Engine:
+    def __init__(self, No, Nv, device=0, rank=0, nranks=1, with_J=False, batch_tuples=0, resident=True):
+        self.L = load_library()
+        self.No, self.Nv = int(No), int(Nv)
+        cfg = Config(device, rank, nranks, int(with_J), No, Nv, batch_tuples, int(resident), 0)
+        self.ctx = C.c_void_p()
+        self._ck(self.L.atrip_b200_create(C.byref(self.ctx), C.byref(cfg)))
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise EngineError(self.L.atrip_b200_last_error().decode())
+
+    def close(self):
+        if getattr(self, "ctx", None) and self.ctx.value:
+            self.L.atrip_b200_destroy(self.ctx)
+            self.ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # ---- data
+    def set_epsilon(self, eps_i, eps_a):
+        self._ck(self.L.atrip_b200_set_epsilon(self.ctx, _ptr(eps_i), _ptr(eps_a)))
+
+    def set_Tai(self, Tai):
+        self._ck(self.L.atrip_b200_set_Tai(self.ctx, _ptr(Tai)))
+
+    def load(self, name, host):
+        self._ck(getattr(self.L, "atrip_b200_load_" + name)(self.ctx, _ptr(host)))
+
+    def load_all(self, eps_i, eps_a, Tai, Tabij, Vabij, Vijka, Vabci, Jijka=None, Jabci=None):
+        self.set_epsilon(eps_i, eps_a)
+        self.set_Tai(Tai)
+        self.load("Tabij", Tabij)
+        self.load("Vabij", Vabij)
+        self.load("Vijka", Vijka)
+        self.load("Vabci", Vabci)
+        if Jijka is not None:
+            self.load("Jijka", Jijka)
+        if Jabci is not None:
+            self.load("Jabci", Jabci)
+
+    def fill_synthetic(self, seed=12345, scale=0.1):
+        self._ck(self.L.atrip_b200_fill_synthetic(self.ctx, seed, scale))
+
+    # ---- tuples
+    def build_tuples(self, distribution=GROUP_AND_SORT):
+        self._ck(self.L.atrip_b200_build_tuples(self.ctx, distribution))
+        return self.num_tuples()
+
+    def set_tuples(self, abc):
+        abc = np.ascontiguousarray(abc, dtype=np.uint64).reshape(-1, 3)
+        self._ck(self.L.atrip_b200_set_tuples(self.ctx, abc.ctypes.data_as(_up), len(abc)))
+
+    def num_tuples(self):
+        return self.L.atrip_b200_num_tuples(self.ctx)
+
+    def get_tuples(self):
+        n = self.num_tuples()
+        out = np.empty((n, 3), dtype=np.uint64)
+        self._ck(self.L.atrip_b200_get_tuples(self.ctx, out.ctypes.data_as(_up), n))
+        return out
+
+    # ---- execute
+    def run(self, first=0, count=None):
+        if count is None:
+            count = self.num_tuples() - first
+        e, ct = C.c_double(0), C.c_double(0)
+        self._ck(self.L.atrip_b200_run(self.ctx, first, count, C.byref(e), C.byref(ct)))
+        return e.value, ct.value
+
+    def tuple_debug(self, a, b, c, cubes=True):
+        n = self.No ** 3
+        T = np.empty(n) if cubes else None
+        Z = np.empty(n) if cubes else None
+        e = C.c_double(0)
+        self._ck(self.L.atrip_b200_tuple_debug(self.ctx, a, b, c, _ptr(T), _ptr(Z), C.byref(e)))
+        return e.value, T, Z
+
+    def read_slice(self, kind, x, y=0):
+        No, Nv = self.No, self.Nv
+        n = {TA: Nv * No * No, VIJKA: No ** 3, VABCI: Nv * No, TABIJ: No * No, VABIJ: No * No}[kind]
+        out = np.empty(n)
+        self._ck(self.L.atrip_b200_read_slice(self.ctx, kind, x, y, _ptr(out)))
+        return out
+
+    def last_timing(self):
+        out = (C.c_double * 6)()
+        self.L.atrip_b200_last_timing(self.ctx, out)
+        return dict(total_ms=out[0], contract_ms=out[1], reduce_ms=out[2], contract_launches=int(out[3]),
+                    reduce_launches=int(out[4]), tuples=int(out[5]))
+
+    @property
+    def kp(self):
+        return self.L.atrip_b200_kp(self.ctx)
+
+    @property
+    def flops_per_tuple(self):
+        return self.L.atrip_b200_flops_per_tuple(self.ctx)

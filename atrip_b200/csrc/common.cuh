@@ -1,0 +1,101 @@
+// Shared device/host helpers of the B200 engine.
+#pragma once
+#include <cstdint>
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+namespace ab {
+
+// K (contraction) chunk held by one 128-byte shared-memory row: 16 doubles.  This is the inner
+// box extent of every TMA tensor map (CU_TENSOR_MAP_SWIZZLE_128B needs inner bytes <= 128).
+constexpr int KC = 16;
+
+// ---------------------------------------------------------------------------------------------
+// Counter-based synthetic inputs: value = f(seed, tensor id, column-major linear index).
+// Same specification as the oracle (oracle/atrip_oracle.c: oracle_synth); written
+// independently here.  splitmix64 finaliser, 53-bit mantissa -> u in [0,1).
+//   eps_i = -2 + 1.5 u, eps_a = 0.5 + 3.5 u, everything else = scale * (u - 0.5).
+// The explicit __dmul_rn/__dadd_rn keep nvcc from contracting to an FMA, so host (gcc, no FMA
+// contraction on x86-64 baseline) and device produce bit-identical values.
+enum TensorId : int {
+  T_EPS_I = 0, T_EPS_A = 1, T_TAI = 2, T_TABIJ = 3, T_VABIJ = 4,
+  T_VIJKA = 5, T_VABCI = 6, T_JIJKA = 7, T_JABCI = 8
+};
+
+__host__ __device__ __forceinline__ uint64_t mix64(uint64_t z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+__host__ __device__ __forceinline__ uint64_t synth_key(uint64_t seed, int tensor_id) {
+  return mix64(seed ^ mix64((uint64_t)tensor_id));
+}
+__host__ __device__ __forceinline__ double synth_u(uint64_t key, uint64_t idx) {
+  return (double)(mix64(key + idx) >> 11) * (1.0 / 9007199254740992.0);
+}
+__device__ __forceinline__ double synth_val(uint64_t key, uint64_t idx, double scale) {
+  return __dmul_rn(scale, __dadd_rn(synth_u(key, idx), -0.5));
+}
+
+// ---------------------------------------------------------------------------------------------
+// mbarrier / TMA / DMMA PTX wrappers (sm_100a)
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra LAB_DONE;\n"
+      "bra LAB_WAIT;\n"
+      "LAB_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *tm) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *tm, uint64_t *bar, int c0, int c1,
+                                            int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *tm, uint64_t *bar, int c0, int c1,
+                                            int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
+      "r"(c3)
+      : "memory");
+}
+// D(8x8) += A(8x4, row) * B(4x8, col); SASS: DMMA.8x8x4.  Per thread (g = lane/4, t = lane%4):
+// a = A[g][t], b = B[t][g], d0/d1 = D[g][2t], D[g][2t+1].
+__device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
+}  // namespace ab

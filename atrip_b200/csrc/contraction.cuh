@@ -1,0 +1,202 @@
+// Kernel 1 of the (T) hot path: the doubles contraction.
+//
+// Replaces doubles_contribution (reference Equations.cxx:455-728): 12 xgemm calls
+// (Blas.cxx:46-130) + 12 reorder<perm> accumulations (Equations.cxx:26-83) + 3 copies +
+// 3 memsets per tuple.  Here one persistent launch processes a whole batch of tuples, and per
+// tuple the twelve terms collapse to THREE FP64 tensor-core GEMMs of shape
+// [No^2 x 2Kp] x [2Kp x No] (Kp = Nv + No padded to 16), because with
+//     A_x[(p,q), kappa] = [ T_x[E,p,q] ; -H_x[q,p,L] ]            (kappa = E, then Nv + L)
+//     B_yz[kappa, r]    = [ V_yz[E,r] ; T_yz[L,r] or T_zy[r,L] ]
+// the reference's terms are
+//     C_k[i + j No, k] = A_a [(i,j),:] B_bc + A_b^T[(i,j),:] B_ac      (P1 + H5, P5 + H3)
+//     C_j[i + k No, j] = A_a [(i,k),:] B_cb + A_c^T[(i,k),:] B_ab      (P2 + H6, P3 + H1)
+//     C_i[j + k No, i] = A_b [(j,k),:] B_ca + A_c^T[(j,k),:] B_ba      (P6 + H4, P4 + H2)
+//     Tijk[i,j,k]      = C_k[i,j,k] + C_j[i,k,j] + C_i[j,k,i]
+// with A^T[(u,v),:] = A[(v,u),:].  The "transposition" is only a second TMA tensor map over the
+// same HBM store with the two row strides exchanged -- the permutations live in the operand
+// index maps, there is no reorder pass and no scratch GEMM output that gets re-accumulated.
+//
+// Structure (per CTA, persistent over work items = (tuple, class, row tile, column tile)):
+//   warp NW        : producer; one lane issues cp.async.bulk.tensor (TMA, SWIZZLE_128B) for the
+//                    A tile [No*tv rows x 16] and the B tile [<=NI*8 rows x 16] of each K chunk
+//                    into an nstages-deep ring guarded by full/empty mbarriers; it runs ahead
+//                    across work items so the pipe never drains between tiles.
+//   warps 0..NW-1  : consumers; each owns MI x NI DMMA.8x8x4 accumulator fragments
+//                    (rows [w*MI*8, (w+1)*MI*8) of the tile), loads fragments with LDS.64 from
+//                    the swizzled rows (conflict free: fragment row g <-> tile row 2(g%4)+g/4),
+//                    and stores its C fragments straight to the class cube in HBM/L2.
+#pragma once
+#include "common.cuh"
+
+namespace ab {
+
+constexpr int MAX_STAGES = 12;
+
+struct ContractParams {
+  int No, Nv, Kp;
+  int nk;       // Kp / KC: K chunks per operand pair (a class runs 2*nk chunks)
+  int tv;       // tile = all u (No) x tv values of v  ->  No*tv rows
+  int mtiles;   // ceil(No / tv)
+  int ntiles;   // ceil(No / (NI*8))
+  int arows;    // shared-memory rows reserved for A per stage = NW*MI*8 >= No*tv
+  int brows;    // rows of the B TMA box (min(NI*8, No))
+  int nstages;
+  int ntuples;
+  const int4 *tuples;  // (a, b, c, -) of the batch
+  const int *xtab;     // virtual index x -> slot in the AX store
+  const int *btab;     // pair index (y + z Nv, or Nv^2 + y for the transposed diagonal) -> BY slot
+  double *R;           // [ntuples][3][No^3] class cubes C_k, C_j, C_i
+};
+
+__host__ __device__ inline size_t contract_stage_bytes(int arows, int NI) {
+  return (size_t)(arows + NI * 8) * 128;
+}
+
+template <int MI, int NI, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1)
+contract_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAT,
+                const __grid_constant__ CUtensorMap tmB, const ContractParams P) {
+  extern __shared__ unsigned char smem_raw[];
+  __shared__ uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES];
+
+  const int nwarps = (blockDim.x >> 5) - 1;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned char *base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const size_t stage_bytes = contract_stage_bytes(P.arows, NI);
+
+  // zero the ring once: rows the TMA boxes never write (B rows >= brows, A rows >= No*tv) must
+  // not hold NaN patterns from a previous kernel
+  {
+    const size_t n16 = stage_bytes * P.nstages / 16;
+    uint4 *z = reinterpret_cast<uint4 *>(base);
+    for (size_t i = threadIdx.x; i < n16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
+  }
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < P.nstages; s++) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], nwarps);
+    }
+    fence_barrier_init();
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmAT);
+    tma_prefetch_desc(&tmB);
+  }
+  fence_proxy_async();
+  __syncthreads();
+
+  const long long per_tuple = 3LL * P.mtiles * P.ntiles;
+  const long long nitems = per_tuple * P.ntuples;
+  const size_t cube = (size_t)P.No * P.No * P.No;
+  int stage = 0;
+  uint32_t phase = 0;
+
+  if (warp == nwarps) {
+    // ------------------------------------------------------------------ producer
+    if (lane == 0) {
+      const uint32_t tx = (uint32_t)((P.No * P.tv + P.brows) * 128);
+      const int NvNv = P.Nv * P.Nv;
+      for (long long item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const int tup = (int)(item / per_tuple);
+        int rem = (int)(item - (long long)tup * per_tuple);
+        const int cls = rem / (P.mtiles * P.ntiles);
+        rem -= cls * P.mtiles * P.ntiles;
+        const int mt = rem / P.ntiles, nt = rem - mt * P.ntiles;
+        const int4 abc = P.tuples[tup];
+        if (abc.x == 0 && abc.y == 0 && abc.z == 0) continue;  // FAKE_TUPLE (Tuples.hpp:43)
+        const int a = abc.x, b = abc.y, c = abc.z;
+        // operands per class: {x plain, (y,z) of its B, transposed-hole flag}, {x transposed, ...}
+        int xs[2], ys[2], zs[2], fs[2];
+        if (cls == 0) { xs[0] = a; ys[0] = b; zs[0] = c; fs[0] = 0; xs[1] = b; ys[1] = a; zs[1] = c; fs[1] = 0; }
+        else if (cls == 1) { xs[0] = a; ys[0] = c; zs[0] = b; fs[0] = 1; xs[1] = c; ys[1] = a; zs[1] = b; fs[1] = 0; }
+        else { xs[0] = b; ys[0] = c; zs[0] = a; fs[0] = 1; xs[1] = c; ys[1] = b; zs[1] = a; fs[1] = 1; }
+#pragma unroll
+        for (int piece = 0; piece < 2; piece++) {
+          const int xslot = P.xtab[xs[piece]];
+          const int bidx = (ys[piece] == zs[piece] && fs[piece]) ? NvNv + ys[piece]
+                                                                : ys[piece] + zs[piece] * P.Nv;
+          const int bslot = P.btab[bidx];
+          const CUtensorMap *tm = piece ? &tmAT : &tmA;
+          for (int kc = 0; kc < P.nk; kc++) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            unsigned char *sb = base + (size_t)stage * stage_bytes;
+            mbar_expect_tx(&full_bar[stage], tx);
+            tma_load_4d(sb, tm, &full_bar[stage], kc * KC, 0, mt * P.tv, xslot);
+            tma_load_3d(sb + (size_t)P.arows * 128, &tmB, &full_bar[stage], kc * KC, nt * NI * 8, bslot);
+            if (++stage == P.nstages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+    return;
+  }
+
+  // -------------------------------------------------------------------- consumers
+  const int g = lane >> 2, t = lane & 3;
+  const int perm = 2 * (g & 3) + (g >> 2);  // tile row (mod 8) held by fragment row g
+  const uint32_t offA = (uint32_t)((warp * MI * 8 + perm) * 128 + (t & 1) * 8);
+  const uint32_t offB = (uint32_t)((P.arows + perm) * 128 + (t & 1) * 8);
+  uint32_t cs[4];
+#pragma unroll
+  for (int s = 0; s < 4; s++) cs[s] = (uint32_t)(((2 * s + (t >> 1)) ^ perm) * 16);
+  const int nchunks = 2 * P.nk;
+  const int tile_rows = P.No * P.tv;
+
+  for (long long item = blockIdx.x; item < nitems; item += gridDim.x) {
+    const int tup = (int)(item / per_tuple);
+    int rem = (int)(item - (long long)tup * per_tuple);
+    const int cls = rem / (P.mtiles * P.ntiles);
+    rem -= cls * P.mtiles * P.ntiles;
+    const int mt = rem / P.ntiles, nt = rem - mt * P.ntiles;
+    const int4 abc = P.tuples[tup];
+    if (abc.x == 0 && abc.y == 0 && abc.z == 0) continue;
+
+    double acc[MI][NI][2];
+#pragma unroll
+    for (int i = 0; i < MI; i++)
+#pragma unroll
+      for (int j = 0; j < NI; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    for (int ch = 0; ch < nchunks; ch++) {
+      mbar_wait(&full_bar[stage], phase);
+      const unsigned char *sb = base + (size_t)stage * stage_bytes;
+#pragma unroll
+      for (int s = 0; s < 4; s++) {
+        double af[MI], bf[NI];
+#pragma unroll
+        for (int i = 0; i < MI; i++) af[i] = *reinterpret_cast<const double *>(sb + offA + i * 1024 + cs[s]);
+#pragma unroll
+        for (int j = 0; j < NI; j++) bf[j] = *reinterpret_cast<const double *>(sb + offB + j * 1024 + cs[s]);
+#pragma unroll
+        for (int i = 0; i < MI; i++)
+#pragma unroll
+          for (int j = 0; j < NI; j++) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[stage]);
+      if (++stage == P.nstages) { stage = 0; phase ^= 1; }
+    }
+
+    // epilogue: C fragment (row g, cols 2t, 2t+1) -> tile row/col through the same permutation
+    double *Rc = P.R + ((size_t)tup * 3 + cls) * cube;
+    const int m0 = mt * tile_rows;
+    const int NoNo = P.No * P.No;
+#pragma unroll
+    for (int i = 0; i < MI; i++) {
+      const int rl = warp * MI * 8 + i * 8 + perm;
+      const int m = m0 + rl;
+      if (rl < tile_rows && m < NoNo) {
+#pragma unroll
+        for (int j = 0; j < NI; j++) {
+#pragma unroll
+          for (int e = 0; e < 2; e++) {
+            const int cf = 2 * t + e;
+            const int col = nt * NI * 8 + j * 8 + 2 * (cf & 3) + (cf >> 2);
+            if (col < P.No) Rc[(size_t)m + (size_t)col * NoNo] = acc[i][j][e];
+          }
+        }
+      }
+    }
+  }
+}
+
+}  // namespace ab

@@ -1,0 +1,779 @@
+// The B200 device engine behind include/atrip_b200.h: context, HBM stores, tuple lists, the
+// batch loop over the two hot kernels (contraction.cuh, reduction.cuh) and the C-ABI.
+//
+// There is deliberately no CPU path in this file: every compute entry point needs the CUDA
+// device and fails loudly without it.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/atrip_b200.h"
+#include "common.cuh"
+#include "contraction.cuh"
+#include "reduction.cuh"
+#include "stores.cuh"
+#include "tuples.hpp"
+
+using namespace ab;
+
+namespace {
+
+thread_local std::string g_error;
+
+struct Fail {
+  std::string msg;
+};
+#define CUDA_OK(expr)                                                                              \
+  do {                                                                                             \
+    cudaError_t e__ = (expr);                                                                      \
+    if (e__ != cudaSuccess)                                                                        \
+      throw Fail{std::string("CUDA: ") + cudaGetErrorString(e__) + " in " #expr " (" __FILE__ ":" + \
+                 std::to_string(__LINE__) + ")"};                                                  \
+  } while (0)
+#define REQUIRE(cond, text)                 \
+  do {                                      \
+    if (!(cond)) throw Fail{std::string(text)}; \
+  } while (0)
+
+// ------------------------------------------------------------------ contraction kernel registry
+struct KernelVariant {
+  int MI, NI, maxt;
+  const void *fn;
+};
+#define VARIANT(mi, ni, maxt) KernelVariant{mi, ni, maxt, (const void *)contract_kernel<mi, ni, maxt>}
+const KernelVariant kVariants[] = {
+    VARIANT(2, 1, 512), VARIANT(2, 2, 512), VARIANT(2, 3, 512), VARIANT(2, 4, 512), VARIANT(2, 5, 512),
+    VARIANT(2, 6, 512), VARIANT(2, 7, 512), VARIANT(2, 8, 512), VARIANT(2, 10, 416), VARIANT(2, 13, 416),
+    VARIANT(4, 4, 512), VARIANT(4, 5, 384), VARIANT(4, 6, 352), VARIANT(4, 8, 288),
+};
+
+struct ContractPlan {
+  const KernelVariant *k = nullptr;
+  int nw = 0, tv = 0, mtiles = 0, ntiles = 0, arows = 0, brows = 0, nstages = 0;
+  size_t smem = 0;
+  double useful = 0;
+};
+
+ContractPlan plan_contraction(int No, size_t smem_limit) {
+  ContractPlan best;
+  double best_score = -1;
+  for (const auto &k : kVariants) {
+    const int ntiles = (No + k.NI * 8 - 1) / (k.NI * 8);
+    for (int nw = 2; nw <= k.maxt / 32 - 1; nw++) {
+      const int arows = nw * k.MI * 8;
+      int tv = std::min(No, arows / No);
+      if (tv < 1) continue;
+      tv = std::min(tv, 256);
+      const int mtiles = (No + tv - 1) / tv;
+      const size_t stage = contract_stage_bytes(arows, k.NI);
+      int nstages = (int)std::min<size_t>(MAX_STAGES, (smem_limit - 2048) / stage);
+      if (nstages < 3) continue;
+      const double useful = (double)No * No * No / ((double)mtiles * arows * ntiles * k.NI * 8);
+      // measured (tools/fp64_peak.cu): 4 consumer warps reach ~89 % of DMMA peak, >= 8 reach it
+      const double warp_eff = nw >= 8 ? 1.0 : (nw >= 6 ? 0.97 : (nw >= 4 ? 0.89 : 0.6));
+      // fewer LDS per DMMA and fewer barrier trips with larger fragments grids
+      const double frag_eff = 1.0 - 0.04 / (k.MI * k.NI) * 8;
+      const double score = useful * warp_eff * frag_eff;
+      if (score > best_score + 1e-9) {
+        best_score = score;
+        best.k = &k;
+        best.nw = nw;
+        best.tv = tv;
+        best.mtiles = mtiles;
+        best.ntiles = ntiles;
+        best.arows = arows;
+        best.brows = std::min(k.NI * 8, No);
+        best.nstages = nstages;
+        best.smem = stage * nstages + 1024;
+        best.useful = useful;
+      }
+    }
+  }
+  return best;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CUDA_OK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
+    REQUIRE(p && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available from the driver");
+    fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+void make_map(CUtensorMap *tm, void *base, int rank, const uint64_t *dims, const uint64_t *strides_bytes,
+              const uint32_t *box) {
+  cuuint64_t gdim[5], gstr[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; i++) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+    if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
+  }
+  CUresult r = encode_tiled()(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, (cuuint32_t)rank, base, gdim, gstr, bx, es,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw Fail{"cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r)};
+}
+
+template <typename T>
+T *dalloc(size_t n) {
+  T *p = nullptr;
+  CUDA_OK(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
+  return p;
+}
+
+}  // namespace
+
+struct atrip_b200_ctx {
+  atrip_b200_config cfg{};
+  int No = 0, Nv = 0, Kp = 0;
+  int nsm = 0;
+  size_t smem_limit = 0;
+  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  cudaEvent_t ev[6]{};
+
+  // stores
+  size_t nX = 0, nB = 0, nV = 0;
+  double *AX = nullptr, *BY = nullptr, *VIJ = nullptr;
+  double *AXJ = nullptr, *BYJ = nullptr;  // (cT): J tensors in the same layouts
+  double *eps_i = nullptr, *eps_a = nullptr, *Tai = nullptr;
+  int *xtab = nullptr, *btab = nullptr, *vtab = nullptr;
+  int *xlist = nullptr, *ylist = nullptr, *zlist = nullptr, *tflag = nullptr, *vy = nullptr, *vz = nullptr;
+  bool have_J = false;
+
+  // tuples
+  std::vector<Tuple> tuples;
+  int4 *d_tuples = nullptr;
+  size_t d_tuples_cap = 0;
+
+  // work buffers
+  int batch = 0;
+  double *R = nullptr, *RJ = nullptr, *e_tuple = nullptr, *d_total = nullptr;
+  int4 *dbg_tuple = nullptr;
+
+  // kernel plan
+  ContractPlan plan;
+  CUtensorMap tmA, tmAT, tmB, tmAJ, tmATJ, tmBJ;
+
+  // staging for ingest
+  double *h_stage[2] = {nullptr, nullptr}, *d_stage[2] = {nullptr, nullptr};
+  size_t stage_elems = 0;
+  cudaEvent_t stage_ev[2]{};
+
+  double timing[6] = {0, 0, 0, 0, 0, 0};
+};
+
+namespace {
+
+StoreDims dims_of(const atrip_b200_ctx *c) { return StoreDims{c->No, c->Nv, c->Kp}; }
+
+void build_maps(atrip_b200_ctx *c, double *AX, double *BY, CUtensorMap *tA, CUtensorMap *tAT, CUtensorMap *tB) {
+  const uint64_t No = c->No, Kp = c->Kp;
+  {
+    const uint64_t dims[4] = {Kp, No, No, c->nX};
+    const uint64_t strP[3] = {Kp * 8, No * Kp * 8, No * No * Kp * 8};
+    const uint64_t strT[3] = {No * Kp * 8, Kp * 8, No * No * Kp * 8};
+    const uint32_t box[4] = {KC, (uint32_t)No, (uint32_t)c->plan.tv, 1};
+    make_map(tA, AX, 4, dims, strP, box);
+    make_map(tAT, AX, 4, dims, strT, box);
+  }
+  {
+    const uint64_t dims[3] = {Kp, No, c->nB};
+    const uint64_t str[2] = {Kp * 8, No * Kp * 8};
+    const uint32_t box[3] = {KC, (uint32_t)c->plan.brows, 1};
+    make_map(tB, BY, 3, dims, str, box);
+  }
+}
+
+void ensure_stage(atrip_b200_ctx *c, size_t elems) {
+  if (c->stage_elems >= elems) return;
+  for (int i = 0; i < 2; i++) {
+    if (c->h_stage[i]) cudaFreeHost(c->h_stage[i]);
+    if (c->d_stage[i]) cudaFree(c->d_stage[i]);
+    CUDA_OK(cudaMallocHost(&c->h_stage[i], elems * sizeof(double)));
+    c->d_stage[i] = dalloc<double>(elems);
+    if (!c->stage_ev[i]) CUDA_OK(cudaEventCreateWithFlags(&c->stage_ev[i], cudaEventDisableTiming));
+  }
+  c->stage_elems = elems;
+}
+
+bool is_pinned(const void *p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return at.type == cudaMemoryTypeHost;
+}
+
+// stream a host tensor through the double-buffered staging pair, one chunk at a time;
+// `consume(chunk_index, device_ptr)` enqueues the re-tiling kernel on c->stream
+template <typename F>
+void stream_chunks(atrip_b200_ctx *c, const double *host, size_t nchunks, size_t chunk_elems, F consume) {
+  ensure_stage(c, chunk_elems);
+  const bool pinned = is_pinned(host);
+  for (size_t k = 0; k < nchunks; k++) {
+    const int s = (int)(k & 1);
+    // the kernel that last read d_stage[s] (and the copy out of h_stage[s]) must be done
+    CUDA_OK(cudaEventSynchronize(c->stage_ev[s]));
+    const double *src = host + k * chunk_elems;
+    if (!pinned) {
+      std::memcpy(c->h_stage[s], src, chunk_elems * sizeof(double));
+      src = c->h_stage[s];
+    }
+    CUDA_OK(cudaMemcpyAsync(c->d_stage[s], src, chunk_elems * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    consume(k, c->d_stage[s]);
+    CUDA_OK(cudaEventRecord(c->stage_ev[s], c->stream));
+  }
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+}
+
+void launch_contract(atrip_b200_ctx *c, const int4 *d_tuples, int ntuples, bool useJ) {
+  ContractParams P;
+  P.No = c->No;
+  P.Nv = c->Nv;
+  P.Kp = c->Kp;
+  P.nk = c->Kp / KC;
+  P.tv = c->plan.tv;
+  P.mtiles = c->plan.mtiles;
+  P.ntiles = c->plan.ntiles;
+  P.arows = c->plan.arows;
+  P.brows = c->plan.brows;
+  P.nstages = c->plan.nstages;
+  P.ntuples = ntuples;
+  P.tuples = d_tuples;
+  P.xtab = c->xtab;
+  P.btab = c->btab;
+  P.R = useJ ? c->RJ : c->R;
+  const long long nitems = 3LL * P.mtiles * P.ntiles * ntuples;
+  const int grid = (int)std::min<long long>(c->nsm, nitems);
+  if (grid <= 0) return;
+  void *args[4] = {useJ ? (void *)&c->tmAJ : (void *)&c->tmA, useJ ? (void *)&c->tmATJ : (void *)&c->tmAT,
+                   useJ ? (void *)&c->tmBJ : (void *)&c->tmB, (void *)&P};
+  CUDA_OK(cudaLaunchKernel(c->plan.k->fn, dim3(grid), dim3((c->plan.nw + 1) * 32), args, c->plan.smem, c->stream));
+}
+
+ReduceParams reduce_params(atrip_b200_ctx *c, const int4 *d_tuples, int ntuples, bool ct) {
+  ReduceParams P;
+  P.No = c->No;
+  P.Nv = c->Nv;
+  P.ntuples = ntuples;
+  P.tuples = d_tuples;
+  P.R = ct ? c->RJ : c->R;
+  P.RZ = c->R;
+  P.eps_i = c->eps_i;
+  P.eps_a = c->eps_a;
+  P.Tai = c->Tai;
+  P.VIJ = c->VIJ;
+  P.vtab = c->vtab;
+  P.e_tuple = c->e_tuple;
+  return P;
+}
+
+void launch_reduce(atrip_b200_ctx *c, const int4 *d_tuples, int ntuples, bool ct, double *total) {
+  if (ntuples <= 0) return;
+  ReduceParams P = reduce_params(c, d_tuples, ntuples, ct);
+  const size_t smem = reduce_smem_bytes(c->No, ct);
+  if (ct) reduce_kernel<true><<<ntuples, REDUCE_THREADS, smem, c->stream>>>(P);
+  else reduce_kernel<false><<<ntuples, REDUCE_THREADS, smem, c->stream>>>(P);
+  CUDA_OK(cudaGetLastError());
+  accumulate_kernel<<<1, 256, 0, c->stream>>>(c->e_tuple, ntuples, total);
+  CUDA_OK(cudaGetLastError());
+}
+
+void upload_tuples(atrip_b200_ctx *c) {
+  const size_t n = c->tuples.size();
+  if (n > c->d_tuples_cap) {
+    if (c->d_tuples) cudaFree(c->d_tuples);
+    c->d_tuples = dalloc<int4>(n);
+    c->d_tuples_cap = n;
+  }
+  std::vector<int4> h(n);
+  for (size_t i = 0; i < n; i++) h[i] = make_int4((int)c->tuples[i][0], (int)c->tuples[i][1], (int)c->tuples[i][2], 0);
+  CUDA_OK(cudaMemcpy(c->d_tuples, h.data(), n * sizeof(int4), cudaMemcpyHostToDevice));
+}
+
+void create_impl(atrip_b200_ctx *c) {
+  const auto &cfg = c->cfg;
+  REQUIRE(cfg.No >= 1 && cfg.Nv >= 1, "No and Nv must be positive");
+  REQUIRE(cfg.No <= 256, "No > 256 is not supported by the TMA box of the contraction kernel");
+  REQUIRE(cfg.nranks >= 1 && cfg.rank >= 0 && cfg.rank < cfg.nranks, "bad rank / nranks");
+  REQUIRE(cfg.Nv * cfg.Nv + cfg.Nv < (1LL << 31), "Nv too large for 32-bit pair tables");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    throw Fail{std::string("no usable CUDA device (") + cudaGetErrorString(e) +
+               "); the atrip_b200 engine has no CPU fallback"};
+  REQUIRE(cfg.device >= 0 && cfg.device < ndev, "device ordinal out of range");
+  CUDA_OK(cudaSetDevice(cfg.device));
+  cudaDeviceProp prop;
+  CUDA_OK(cudaGetDeviceProperties(&prop, cfg.device));
+  REQUIRE(prop.major >= 10, "atrip_b200 needs an sm_100a device (B200)");
+  c->nsm = prop.multiProcessorCount;
+  c->smem_limit = prop.sharedMemPerBlockOptin;
+  c->No = (int)cfg.No;
+  c->Nv = (int)cfg.Nv;
+  c->Kp = (int)((cfg.No + cfg.Nv + KC - 1) / KC * KC);
+  CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CUDA_OK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  for (auto &ev : c->ev) CUDA_OK(cudaEventCreate(&ev));
+
+  c->plan = plan_contraction(c->No, c->smem_limit);
+  REQUIRE(c->plan.k, "no contraction kernel variant fits this No");
+  CUDA_OK(cudaFuncSetAttribute(c->plan.k->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->plan.smem));
+  CUDA_OK(cudaFuncSetAttribute((const void *)reduce_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)reduce_smem_bytes(c->No, false)));
+  CUDA_OK(cudaFuncSetAttribute((const void *)reduce_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)reduce_smem_bytes(c->No, true)));
+
+  // ---- slot tables.  resident: every slice lives here.
+  REQUIRE(cfg.resident || cfg.nranks == 1, "non-resident (owned slices + fetch cache) stores: not in this build");
+  const size_t Nv = c->Nv, NvNv = Nv * Nv;
+  std::vector<int> xtab(Nv), xlist(Nv);
+  for (size_t x = 0; x < Nv; x++) xtab[x] = xlist[x] = (int)x;
+  c->nX = Nv;
+  std::vector<int> btab(NvNv + Nv), yl(NvNv + Nv), zl(NvNv + Nv), tf(NvNv + Nv, 0);
+  for (size_t z = 0; z < Nv; z++)
+    for (size_t y = 0; y < Nv; y++) {
+      btab[y + z * Nv] = (int)(y + z * Nv);
+      yl[y + z * Nv] = (int)y;
+      zl[y + z * Nv] = (int)z;
+    }
+  for (size_t y = 0; y < Nv; y++) {
+    btab[NvNv + y] = (int)(NvNv + y);
+    yl[NvNv + y] = zl[NvNv + y] = (int)y;
+    tf[NvNv + y] = 1;
+  }
+  c->nB = NvNv + Nv;
+  std::vector<int> vtab(NvNv, -1), vy, vz;
+  for (size_t z = 0; z < Nv; z++)
+    for (size_t y = 0; y <= z; y++) {
+      vtab[y + z * Nv] = (int)vy.size();
+      vy.push_back((int)y);
+      vz.push_back((int)z);
+    }
+  c->nV = vy.size();
+  auto up = [&](const std::vector<int> &h) {
+    int *d = dalloc<int>(h.size());
+    CUDA_OK(cudaMemcpy(d, h.data(), h.size() * sizeof(int), cudaMemcpyHostToDevice));
+    return d;
+  };
+  c->xtab = up(xtab);
+  c->xlist = up(xlist);
+  c->btab = up(btab);
+  c->ylist = up(yl);
+  c->zlist = up(zl);
+  c->tflag = up(tf);
+  c->vtab = up(vtab);
+  c->vy = up(vy);
+  c->vz = up(vz);
+
+  // ---- stores
+  const size_t No = c->No, Kp = c->Kp;
+  const size_t axn = c->nX * No * No * Kp, byn = c->nB * No * Kp, vn = c->nV * No * No;
+  c->AX = dalloc<double>(axn);
+  c->BY = dalloc<double>(byn);
+  c->VIJ = dalloc<double>(vn);
+  CUDA_OK(cudaMemsetAsync(c->AX, 0, axn * 8, c->stream));
+  CUDA_OK(cudaMemsetAsync(c->BY, 0, byn * 8, c->stream));
+  CUDA_OK(cudaMemsetAsync(c->VIJ, 0, vn * 8, c->stream));
+  if (cfg.with_J) {
+    c->AXJ = dalloc<double>(axn);
+    c->BYJ = dalloc<double>(byn);
+    CUDA_OK(cudaMemsetAsync(c->AXJ, 0, axn * 8, c->stream));
+    CUDA_OK(cudaMemsetAsync(c->BYJ, 0, byn * 8, c->stream));
+  }
+  c->eps_i = dalloc<double>(No);
+  c->eps_a = dalloc<double>(Nv);
+  c->Tai = dalloc<double>(No * Nv);
+
+  // ---- work buffers: a batch keeps roughly 8 work items per SM in flight and <= 1 GiB of cubes
+  const size_t cube3 = 3 * No * No * No;
+  long long batch = cfg.batch_tuples;
+  if (batch <= 0) {
+    const long long per_tuple = 3LL * c->plan.mtiles * c->plan.ntiles;
+    batch = std::max<long long>(c->nsm, (c->nsm * 24LL + per_tuple - 1) / per_tuple * 4);
+    batch = std::min<long long>(batch, std::max<long long>(16, (1LL << 30) / (long long)(cube3 * 8)));
+    batch = (batch + c->nsm - 1) / c->nsm * c->nsm;
+    batch = std::min<long long>(batch, std::max<long long>(16, (1LL << 30) / (long long)(cube3 * 8)));
+  }
+  c->batch = (int)std::max<long long>(1, batch);
+  c->R = dalloc<double>(cube3 * c->batch);
+  if (cfg.with_J) c->RJ = dalloc<double>(cube3 * c->batch);
+  c->e_tuple = dalloc<double>(c->batch);
+  c->d_total = dalloc<double>(2);
+  c->dbg_tuple = dalloc<int4>(1);
+
+  build_maps(c, c->AX, c->BY, &c->tmA, &c->tmAT, &c->tmB);
+  if (cfg.with_J) build_maps(c, c->AXJ, c->BYJ, &c->tmAJ, &c->tmATJ, &c->tmBJ);
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+}
+
+void destroy_impl(atrip_b200_ctx *c) {
+  if (!c) return;
+  cudaSetDevice(c->cfg.device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  void *ptrs[] = {c->AX, c->BY, c->VIJ, c->AXJ, c->BYJ, c->eps_i, c->eps_a, c->Tai, c->xtab, c->btab,
+                  c->vtab, c->xlist, c->ylist, c->zlist, c->tflag, c->vy, c->vz, c->d_tuples, c->R, c->RJ,
+                  c->e_tuple, c->d_total, c->dbg_tuple, c->d_stage[0], c->d_stage[1]};
+  for (void *p : ptrs)
+    if (p) cudaFree(p);
+  for (auto *h : c->h_stage)
+    if (h) cudaFreeHost(h);
+  for (auto &ev : c->ev)
+    if (ev) cudaEventDestroy(ev);
+  for (auto &ev : c->stage_ev)
+    if (ev) cudaEventDestroy(ev);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  delete c;
+}
+
+int grid_for(size_t n, int nsm) { return (int)std::min<size_t>((n + 255) / 256, (size_t)nsm * 16); }
+
+void fill_impl(atrip_b200_ctx *c, uint64_t seed, double scale) {
+  const StoreDims d = dims_of(c);
+  const size_t No = c->No, Kp = c->Kp;
+  fill_small_kernel<<<grid_for(No * (size_t)c->Nv, c->nsm), 256, 0, c->stream>>>(
+      c->eps_i, c->eps_a, c->Tai, d, synth_key(seed, T_EPS_I), synth_key(seed, T_EPS_A), synth_key(seed, T_TAI), scale);
+  fill_AX_kernel<<<grid_for(c->nX * No * No * Kp, c->nsm), 256, 0, c->stream>>>(
+      c->AX, d, c->xlist, (int)c->nX, synth_key(seed, T_TABIJ), synth_key(seed, T_VIJKA), scale);
+  fill_BY_kernel<<<grid_for(c->nB * No * Kp, c->nsm), 256, 0, c->stream>>>(
+      c->BY, d, c->ylist, c->zlist, c->tflag, c->nB, synth_key(seed, T_VABCI), synth_key(seed, T_TABIJ), scale);
+  fill_VIJ_kernel<<<grid_for(c->nV * No * No, c->nsm), 256, 0, c->stream>>>(c->VIJ, d, c->vy, c->vz, c->nV,
+                                                                          synth_key(seed, T_VABIJ), scale);
+  if (c->cfg.with_J) {
+    fill_AX_kernel<<<grid_for(c->nX * No * No * Kp, c->nsm), 256, 0, c->stream>>>(
+        c->AXJ, d, c->xlist, (int)c->nX, synth_key(seed, T_TABIJ), synth_key(seed, T_JIJKA), scale);
+    fill_BY_kernel<<<grid_for(c->nB * No * Kp, c->nsm), 256, 0, c->stream>>>(
+        c->BYJ, d, c->ylist, c->zlist, c->tflag, c->nB, synth_key(seed, T_JABCI), synth_key(seed, T_TABIJ), scale);
+    c->have_J = true;
+  }
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+}
+
+void load_Tabij_impl(atrip_b200_ctx *c, const double *T) {
+  const StoreDims d = dims_of(c);
+  const size_t NvNv = (size_t)c->Nv * c->Nv;
+  const dim3 grid((c->Nv + 31) / 32, (c->Nv + 31) / 32), block(32, 8);
+  stream_chunks(c, T, (size_t)c->No * c->No, NvNv, [&](size_t k, const double *dev) {
+    const int p = (int)(k % c->No), q = (int)(k / c->No);
+    ingest_Tabij_kernel<<<grid, block, 0, c->stream>>>(dev, d, p, q, c->AX, c->xtab, c->BY, c->btab);
+    if (c->cfg.with_J)
+      ingest_Tabij_kernel<<<grid, block, 0, c->stream>>>(dev, d, p, q, c->AXJ, c->xtab, c->BYJ, c->btab);
+  });
+  CUDA_OK(cudaGetLastError());
+}
+
+void load_hhhp_impl(atrip_b200_ctx *c, const double *V, double *AX) {
+  const StoreDims d = dims_of(c);
+  const size_t cube = (size_t)c->No * c->No * c->No;
+  const size_t xper = std::max<size_t>(1, std::min<size_t>(c->Nv, (size_t)(32u << 20) / (cube * 8)));
+  const size_t nchunks = (c->Nv + xper - 1) / xper;
+  ensure_stage(c, xper * cube);
+  // the last chunk may be shorter: stream_chunks copies full chunks, so handle the tail by hand
+  const size_t full = c->Nv / xper;
+  stream_chunks(c, V, full, xper * cube, [&](size_t k, const double *dev) {
+    ingest_Vijka_kernel<<<grid_for(xper * cube, c->nsm), 256, 0, c->stream>>>(dev, d, (int)(k * xper), (int)xper, AX,
+                                                                            c->xtab);
+  });
+  if (full < nchunks) {
+    const size_t x0 = full * xper, nx = c->Nv - x0;
+    CUDA_OK(cudaMemcpyAsync(c->d_stage[0], V + x0 * cube, nx * cube * 8, cudaMemcpyHostToDevice, c->stream));
+    ingest_Vijka_kernel<<<grid_for(nx * cube, c->nsm), 256, 0, c->stream>>>(c->d_stage[0], d, (int)x0, (int)nx, AX,
+                                                                          c->xtab);
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+  }
+  CUDA_OK(cudaGetLastError());
+}
+
+void load_Vabij_impl(atrip_b200_ctx *c, const double *V) {
+  const StoreDims d = dims_of(c);
+  const size_t NvNv = (size_t)c->Nv * c->Nv;
+  stream_chunks(c, V, (size_t)c->No * c->No, NvNv, [&](size_t k, const double *dev) {
+    ingest_Vabij_kernel<<<grid_for(NvNv, c->nsm), 256, 0, c->stream>>>(dev, d, (int)(k % c->No), (int)(k / c->No),
+                                                                     c->VIJ, c->vtab);
+  });
+  CUDA_OK(cudaGetLastError());
+}
+
+void load_ppph_impl(atrip_b200_ctx *c, const double *V, double *BY) {
+  const StoreDims d = dims_of(c);
+  const size_t NvNv = (size_t)c->Nv * c->Nv;
+  // chunk = up to 16 consecutive E for one r: Vabci[:, :, E0.., r]; E blocks never straddle r
+  const int Nv = c->Nv;
+  const int eblocks = (Nv + KC - 1) / KC;
+  ensure_stage(c, (size_t)KC * NvNv);
+  const dim3 grid((unsigned)((NvNv + 31) / 32)), block(32, 8);
+  int slot = 0;
+  for (int r = 0; r < c->No; r++)
+    for (int eb = 0; eb < eblocks; eb++, slot ^= 1) {
+      const int E0 = eb * KC, ne = std::min(KC, Nv - E0);
+      const double *src = V + ((size_t)E0 + (size_t)r * Nv) * NvNv;
+      const size_t n = (size_t)ne * NvNv;
+      CUDA_OK(cudaEventSynchronize(c->stage_ev[slot]));
+      if (!is_pinned(src)) {
+        std::memcpy(c->h_stage[slot], src, n * 8);
+        src = c->h_stage[slot];
+      }
+      CUDA_OK(cudaMemcpyAsync(c->d_stage[slot], src, n * 8, cudaMemcpyHostToDevice, c->stream));
+      ingest_Vabci_kernel<<<grid, block, 0, c->stream>>>(c->d_stage[slot], d, E0, ne, r, BY, c->btab);
+      CUDA_OK(cudaEventRecord(c->stage_ev[slot], c->stream));
+    }
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  CUDA_OK(cudaGetLastError());
+}
+
+void run_impl(atrip_b200_ctx *c, int64_t first, int64_t count, double *energy, double *ct_energy) {
+  REQUIRE(first >= 0 && count >= 0 && (size_t)(first + count) <= c->tuples.size(), "tuple range out of bounds");
+  REQUIRE(c->d_tuples != nullptr || count == 0, "no tuple list: call atrip_b200_build_tuples / set_tuples first");
+  const bool ct = c->have_J;
+  CUDA_OK(cudaMemsetAsync(c->d_total, 0, 2 * sizeof(double), c->stream));
+  cudaEvent_t e_begin = c->ev[0], e_end = c->ev[1];
+  // per-kernel events are recorded around the first batches only (they serialise nothing on one
+  // stream, but keep the count small): contraction [2,3], reduction [4,5]
+  double ms_contract = 0, ms_reduce = 0;
+  int n_contract = 0, n_reduce = 0, sampled = 0;
+  CUDA_OK(cudaEventRecord(e_begin, c->stream));
+  for (int64_t t0 = first; t0 < first + count; t0 += c->batch) {
+    const int nt = (int)std::min<int64_t>(c->batch, first + count - t0);
+    const int4 *tp = c->d_tuples + t0;
+    const bool sample = sampled < 4;
+    if (sample) CUDA_OK(cudaEventRecord(c->ev[2], c->stream));
+    launch_contract(c, tp, nt, false);
+    n_contract++;
+    if (sample) CUDA_OK(cudaEventRecord(c->ev[3], c->stream));
+    launch_reduce(c, tp, nt, false, c->d_total);
+    n_reduce += 2;
+    if (sample) CUDA_OK(cudaEventRecord(c->ev[4], c->stream));
+    if (ct) {
+      launch_contract(c, tp, nt, true);
+      launch_reduce(c, tp, nt, true, c->d_total + 1);
+      n_contract++;
+      n_reduce += 2;
+    }
+    if (sample) {
+      CUDA_OK(cudaEventSynchronize(c->ev[4]));
+      float a = 0, b = 0;
+      CUDA_OK(cudaEventElapsedTime(&a, c->ev[2], c->ev[3]));
+      CUDA_OK(cudaEventElapsedTime(&b, c->ev[3], c->ev[4]));
+      ms_contract += a;
+      ms_reduce += b;
+      sampled++;
+    }
+  }
+  CUDA_OK(cudaEventRecord(e_end, c->stream));
+  double tot[2];
+  CUDA_OK(cudaMemcpyAsync(tot, c->d_total, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  float ms = 0;
+  CUDA_OK(cudaEventElapsedTime(&ms, e_begin, e_end));
+  int64_t real = 0;
+  for (int64_t t = first; t < first + count; t++)
+    real += !(c->tuples[t][0] == 0 && c->tuples[t][1] == 0 && c->tuples[t][2] == 0);
+  c->timing[0] = ms;
+  c->timing[1] = sampled ? ms_contract / sampled : 0;  // mean ms per sampled contraction launch
+  c->timing[2] = sampled ? ms_reduce / sampled : 0;    // mean ms per sampled reduction (+sum) pair
+  c->timing[3] = n_contract;
+  c->timing[4] = n_reduce;
+  c->timing[5] = (double)real;
+  if (energy) *energy = tot[0];
+  if (ct_energy) *ct_energy = ct ? tot[1] : tot[0];  // without J the reference's ct_energy == energy
+}
+
+void tuple_debug_impl(atrip_b200_ctx *c, int64_t a, int64_t b, int64_t cc, double *Tijk, double *Zijk, double *energy) {
+  REQUIRE(a >= 0 && a <= b && b <= cc && cc < c->Nv && !(a == b && b == cc), "not a valid tuple a<=b<=c");
+  const int4 h = make_int4((int)a, (int)b, (int)cc, 0);
+  CUDA_OK(cudaMemcpyAsync(c->dbg_tuple, &h, sizeof(h), cudaMemcpyHostToDevice, c->stream));
+  CUDA_OK(cudaMemsetAsync(c->d_total, 0, 2 * sizeof(double), c->stream));
+  launch_contract(c, c->dbg_tuple, 1, false);
+  launch_reduce(c, c->dbg_tuple, 1, false, c->d_total);
+  const size_t cube = (size_t)c->No * c->No * c->No;
+  double *dT = nullptr, *dZ = nullptr;
+  if (Tijk) dT = dalloc<double>(cube);
+  if (Zijk) dZ = dalloc<double>(cube);
+  if (Tijk || Zijk) {
+    ReduceParams P = reduce_params(c, c->dbg_tuple, 1, false);
+    cubes_kernel<<<grid_for(cube, c->nsm), 256, 0, c->stream>>>(P, 0, dT, dZ);
+    CUDA_OK(cudaGetLastError());
+  }
+  double tot[2];
+  CUDA_OK(cudaMemcpyAsync(tot, c->d_total, sizeof(tot), cudaMemcpyDeviceToHost, c->stream));
+  if (Tijk) CUDA_OK(cudaMemcpyAsync(Tijk, dT, cube * 8, cudaMemcpyDeviceToHost, c->stream));
+  if (Zijk) CUDA_OK(cudaMemcpyAsync(Zijk, dZ, cube * 8, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  if (dT) cudaFree(dT);
+  if (dZ) cudaFree(dZ);
+  if (energy) *energy = tot[0];
+}
+
+void read_slice_impl(atrip_b200_ctx *c, int kind, int64_t x, int64_t y, double *out) {
+  const size_t No = c->No, Nv = c->Nv, Kp = c->Kp;
+  REQUIRE(x >= 0 && x < (int64_t)Nv, "slice index x out of range");
+  size_t n = 0;
+  const double *ax = nullptr, *by = nullptr, *vij = nullptr;
+  if (kind == 100 || kind == 101 || kind == 201) {
+    n = kind == 100 ? Nv * No * No : (kind == 101 ? No * No * No : No * No);
+    ax = c->AX + (size_t)x * No * No * Kp;
+  } else if (kind == 200) {
+    REQUIRE(y >= 0 && y < (int64_t)Nv, "slice index y out of range");
+    n = Nv * No;
+    by = c->BY + ((size_t)x + (size_t)y * Nv) * No * Kp;
+  } else if (kind == 202) {
+    REQUIRE(y >= x && y < (int64_t)Nv, "VABIJ slices are stored for x <= y");
+    n = No * No;
+    std::vector<int> one(1);
+    CUDA_OK(cudaMemcpy(one.data(), c->vtab + x + y * Nv, sizeof(int), cudaMemcpyDeviceToHost));
+    vij = c->VIJ + (size_t)one[0] * No * No;
+  } else {
+    throw Fail{"unknown slice kind"};
+  }
+  if (kind == 201) REQUIRE(y >= 0 && y < (int64_t)Nv, "slice index y out of range");
+  double *d = dalloc<double>(n);
+  read_slice_kernel<<<grid_for(n, c->nsm), 256, 0, c->stream>>>(kind, dims_of(c), ax, by, vij, (int)y, d);
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaMemcpyAsync(out, d, n * 8, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  cudaFree(d);
+}
+
+template <typename F>
+int guarded(atrip_b200_ctx *c, F f) {
+  try {
+    if (c) CUDA_OK(cudaSetDevice(c->cfg.device));
+    f();
+    return 0;
+  } catch (const Fail &e) {
+    g_error = e.msg;
+  } catch (const std::exception &e) {
+    g_error = e.what();
+  }
+  return 1;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *atrip_b200_last_error(void) { return g_error.c_str(); }
+const char *atrip_b200_version(void) { return "atrip_b200 0.1 (sm_100a)"; }
+
+int atrip_b200_create(atrip_b200_ctx **out, const atrip_b200_config *cfg) {
+  if (!out || !cfg) {
+    g_error = "null argument";
+    return 1;
+  }
+  *out = nullptr;
+  atrip_b200_ctx *c = new atrip_b200_ctx();
+  c->cfg = *cfg;
+  const int rc = guarded(nullptr, [&] { create_impl(c); });
+  if (rc) {
+    destroy_impl(c);
+    return rc;
+  }
+  *out = c;
+  return 0;
+}
+
+int atrip_b200_destroy(atrip_b200_ctx *c) {
+  destroy_impl(c);
+  return 0;
+}
+
+int atrip_b200_set_epsilon(atrip_b200_ctx *c, const double *ei, const double *ea) {
+  return guarded(c, [&] {
+    CUDA_OK(cudaMemcpy(c->eps_i, ei, sizeof(double) * c->No, cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(c->eps_a, ea, sizeof(double) * c->Nv, cudaMemcpyHostToDevice));
+  });
+}
+int atrip_b200_set_Tai(atrip_b200_ctx *c, const double *Tai) {
+  return guarded(c, [&] { CUDA_OK(cudaMemcpy(c->Tai, Tai, sizeof(double) * c->No * c->Nv, cudaMemcpyHostToDevice)); });
+}
+int atrip_b200_load_Tabij(atrip_b200_ctx *c, const double *T) { return guarded(c, [&] { load_Tabij_impl(c, T); }); }
+int atrip_b200_load_Vabij(atrip_b200_ctx *c, const double *V) { return guarded(c, [&] { load_Vabij_impl(c, V); }); }
+int atrip_b200_load_Vijka(atrip_b200_ctx *c, const double *V) {
+  return guarded(c, [&] { load_hhhp_impl(c, V, c->AX); });
+}
+int atrip_b200_load_Vabci(atrip_b200_ctx *c, const double *V) {
+  return guarded(c, [&] { load_ppph_impl(c, V, c->BY); });
+}
+int atrip_b200_load_Jijka(atrip_b200_ctx *c, const double *V) {
+  return guarded(c, [&] {
+    REQUIRE(c->cfg.with_J, "context was created without with_J");
+    load_hhhp_impl(c, V, c->AXJ);
+    c->have_J = true;
+  });
+}
+int atrip_b200_load_Jabci(atrip_b200_ctx *c, const double *V) {
+  return guarded(c, [&] {
+    REQUIRE(c->cfg.with_J, "context was created without with_J");
+    load_ppph_impl(c, V, c->BYJ);
+    c->have_J = true;
+  });
+}
+int atrip_b200_fill_synthetic(atrip_b200_ctx *c, uint64_t seed, double scale) {
+  return guarded(c, [&] { fill_impl(c, seed, scale); });
+}
+
+int atrip_b200_build_tuples(atrip_b200_ctx *c, int32_t distribution) {
+  return guarded(c, [&] {
+    REQUIRE(distribution == 0 || distribution == 1, "distribution must be 0 (NAIVE) or 1 (GROUP_AND_SORT)");
+    c->tuples = distribution == 0 ? naive_tuples(c->Nv, c->cfg.rank, c->cfg.nranks)
+                                  : group_and_sort_tuples(c->Nv, c->cfg.rank, c->cfg.nranks, true);
+    upload_tuples(c);
+  });
+}
+int atrip_b200_set_tuples(atrip_b200_ctx *c, const uint64_t *abc, int64_t n) {
+  return guarded(c, [&] {
+    c->tuples.resize((size_t)n);
+    for (int64_t i = 0; i < n; i++) {
+      const uint64_t a = abc[3 * i], b = abc[3 * i + 1], cc = abc[3 * i + 2];
+      const bool fake = a == 0 && b == 0 && cc == 0;
+      REQUIRE(fake || (a <= b && b <= cc && cc < (uint64_t)c->Nv && !(a == b && b == cc)),
+              "tuple " + std::to_string(i) + " is not a<=b<=c<Nv (or the fake tuple)");
+      c->tuples[i] = Tuple{a, b, cc};
+    }
+    upload_tuples(c);
+  });
+}
+int64_t atrip_b200_num_tuples(const atrip_b200_ctx *c) { return c ? (int64_t)c->tuples.size() : 0; }
+int atrip_b200_get_tuples(const atrip_b200_ctx *c, uint64_t *abc, int64_t cap) {
+  const int64_t n = std::min<int64_t>(cap, (int64_t)c->tuples.size());
+  for (int64_t i = 0; i < n; i++)
+    for (int d = 0; d < 3; d++) abc[3 * i + d] = c->tuples[i][d];
+  return 0;
+}
+
+int atrip_b200_run(atrip_b200_ctx *c, int64_t first, int64_t count, double *energy, double *ct_energy) {
+  return guarded(c, [&] { run_impl(c, first, count, energy, ct_energy); });
+}
+int atrip_b200_tuple_debug(atrip_b200_ctx *c, int64_t a, int64_t b, int64_t cc, double *T, double *Z, double *e) {
+  return guarded(c, [&] { tuple_debug_impl(c, a, b, cc, T, Z, e); });
+}
+int atrip_b200_read_slice(atrip_b200_ctx *c, int32_t kind, int64_t x, int64_t y, double *out) {
+  return guarded(c, [&] { read_slice_impl(c, kind, x, y, out); });
+}
+int atrip_b200_last_timing(const atrip_b200_ctx *c, double *out6) {
+  for (int i = 0; i < 6; i++) out6[i] = c->timing[i];
+  return 0;
+}
+int64_t atrip_b200_kp(const atrip_b200_ctx *c) { return c->Kp; }
+double atrip_b200_flops_per_tuple(const atrip_b200_ctx *c) {
+  const double No = c->No, Nv = c->Nv;
+  return 12.0 * No * No * No * (No + Nv);
+}
+
+}  // extern "C"

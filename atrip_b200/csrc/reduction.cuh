@@ -1,0 +1,231 @@
+// Kernel 2 of the (T) hot path: singles + energy denominators + tuple energy, fused.
+//
+// Replaces, per tuple, xcopy Zijk = Tijk (reference Atrip.cxx:899-906), singles_contribution
+// (Equations.cxx:387-426) and get_energy_distinct / get_energy_same (Equations.cxx:101-238),
+// which the reference's GPU path runs as <<<1,1>>> kernels plus a cuMemAlloc and a blocking
+// 8-byte DtoH per tuple (Atrip.cxx:630-676).  Neither Tijk nor Zijk is materialised: one CTA
+// per tuple walks the orbits {I >= J >= K} of 8x8x8 tiles of the occupied cube, rebuilds
+//     Tijk[x,y,z] = C_k[x,y,z] + C_j[x,z,y] + C_i[y,z,x]
+// for the six permuted tiles of the orbit in shared memory (coalesced 64-byte segments from the
+// three class cubes of kernel 1), forms Zijk on the fly from Tai rows and the three Vabij
+// blocks, evaluates the reference's triangular sum k <= j <= i with its weights literally
+// (needed for the a==b / b==c tuples on unsymmetric data), and reduces
+// with warp shuffles to one double per tuple.  The batch sum is a second, single-CTA kernel in a
+// fixed order, so results are run-to-run deterministic and there is no per-tuple DtoH.
+#pragma once
+#include "common.cuh"
+
+namespace ab {
+
+constexpr int RT = 8;                 // tile edge
+constexpr int RS1 = 9, RS2 = 81;      // padded strides of a tile in shared memory
+constexpr int RTILE = 8 * 81 + 8;     // doubles reserved per tile (>= 7 + 7*9 + 7*81 + 1)
+constexpr int REDUCE_THREADS = 256;
+
+struct ReduceParams {
+  int No, Nv;
+  int ntuples;
+  const int4 *tuples;
+  const double *R;    // class cubes giving Tijk           [ntuples][3][No^3]
+  const double *RZ;   // class cubes giving the Tijk inside Zijk (== R except in the cT pass)
+  const double *eps_i, *eps_a, *Tai;
+  const double *VIJ;  // Vabij pair blocks [slot][No^2]
+  const int *vtab;    // y + z Nv -> slot
+  double *e_tuple;    // [ntuples]
+};
+
+__host__ __device__ inline size_t reduce_smem_bytes(int No, bool ct) {
+  return sizeof(double) * ((size_t)(ct ? 12 : 6) * RTILE + 18 * 64 + 4 * (size_t)No + 32);
+}
+
+
+template <bool CT>
+__global__ void __launch_bounds__(REDUCE_THREADS)
+reduce_kernel(const ReduceParams P) {
+  extern __shared__ double sm[];
+  double *Wt = sm;                               // [6][RTILE]
+  double *Zt = CT ? sm + 6 * RTILE : sm;         // [6][RTILE] (aliases Wt when !CT)
+  double *Vb = sm + (CT ? 12 : 6) * RTILE;       // [3][6][64]
+  double *sEps = Vb + 18 * 64;                   // [No]
+  double *sTa = sEps + P.No, *sTb = sTa + P.No, *sTc = sTb + P.No;
+  double *sRed = sTc + P.No;                     // [32]
+
+  const int tup = blockIdx.x;
+  const int4 abc = P.tuples[tup];
+  const int tid = threadIdx.x;
+  if (abc.x == 0 && abc.y == 0 && abc.z == 0) {  // FAKE_TUPLE contributes nothing (Atrip.cxx:629)
+    if (tid == 0) P.e_tuple[tup] = 0.0;
+    return;
+  }
+  const int a = abc.x, b = abc.y, c = abc.z;
+  const int No = P.No, Nv = P.Nv;
+  const size_t NoNo = (size_t)No * No, cube = NoNo * No;
+  const double *Ck = P.R + (size_t)tup * 3 * cube, *Cj = Ck + cube, *Ci = Cj + cube;
+  const double *Zk = P.RZ + (size_t)tup * 3 * cube, *Zj = Zk + cube, *Zi = Zj + cube;
+  const double *Vmat[3] = {P.VIJ + (size_t)P.vtab[b + c * Nv] * NoNo,   // VBCij
+                           P.VIJ + (size_t)P.vtab[a + c * Nv] * NoNo,   // VACij
+                           P.VIJ + (size_t)P.vtab[a + b * Nv] * NoNo};  // VABij
+  for (int i = tid; i < No; i += blockDim.x) {
+    sEps[i] = P.eps_i[i];
+    sTa[i] = P.Tai[a + (size_t)i * Nv];
+    sTb[i] = P.Tai[b + (size_t)i * Nv];
+    sTc[i] = P.Tai[c + (size_t)i * Nv];
+  }
+  const double epsabc = P.eps_a[a] + P.eps_a[b] + P.eps_a[c];  // Atrip.cxx:643-646
+  const bool same = (a == b) != (b == c);                     // Atrip.cxx:640-650
+
+  const int nb = (No + RT - 1) / RT;
+  double esum = 0.0;
+  const int l0 = tid & 7, l1 = (tid >> 3) & 7, l2 = tid >> 6;  // l2 in 0..3
+
+  for (int I = 0; I < nb; I++)
+    for (int J = 0; J <= I; J++)
+      for (int K = 0; K <= J; K++) {
+        const int blk[3] = {I, J, K};
+        __syncthreads();  // previous orbit fully consumed (also publishes sEps.. on first trip)
+        // ---- pass 1: tiles <- C_k[x,y,z] + C_j[x,z,y]   (lanes run along x)
+#pragma unroll
+        for (int X = 0; X < 3; X++)
+#pragma unroll
+          for (int Y = 0; Y < 3; Y++) {
+            if (Y == X) continue;
+            const int Z = 3 - X - Y;
+            const int pi = X * 2 + ((Y > Z) ? 1 : 0);
+            const int x = blk[X] * RT + l0, y = blk[Y] * RT + l1;
+#pragma unroll
+            for (int it = 0; it < 2; it++) {
+              const int zl = l2 + 4 * it, z = blk[Z] * RT + zl;
+              double w = 0.0, wz = 0.0;
+              if (x < No && y < No && z < No) {
+                const size_t i1 = x + (size_t)y * No + (size_t)z * NoNo, i2 = x + (size_t)z * No + (size_t)y * NoNo;
+                w = Ck[i1] + Cj[i2];
+                if (CT) wz = Zk[i1] + Zj[i2];
+              }
+              Wt[pi * RTILE + l0 + RS1 * l1 + RS2 * zl] = w;
+              if (CT) Zt[pi * RTILE + l0 + RS1 * l1 + RS2 * zl] = wz;
+            }
+          }
+        // ---- Vabij blocks: Vb[mat][pair(X,Y)][xl + 8 yl] = Vmat[x + y No]
+        for (int e = tid; e < 18 * 64; e += REDUCE_THREADS) {
+          const int mat = e / 384, r = e - mat * 384, pr = r >> 6, xl = r & 7, yl = (r >> 3) & 7;
+          const int X = pr >> 1, Y = (pr & 1) ? (X == 2 ? 1 : 2) : (X == 0 ? 1 : 0);
+          const int x = blk[X] * RT + xl, y = blk[Y] * RT + yl;
+          Vb[e] = (x < No && y < No) ? Vmat[mat][x + (size_t)y * No] : 0.0;
+        }
+        __syncthreads();
+        // ---- pass 2: tiles += C_i[y,z,x]   (lanes run along y)
+#pragma unroll
+        for (int X = 0; X < 3; X++)
+#pragma unroll
+          for (int Y = 0; Y < 3; Y++) {
+            if (Y == X) continue;
+            const int Z = 3 - X - Y;
+            const int pi = X * 2 + ((Y > Z) ? 1 : 0);
+            const int y = blk[Y] * RT + l0, z = blk[Z] * RT + l1;
+#pragma unroll
+            for (int it = 0; it < 2; it++) {
+              const int xl = l2 + 4 * it, x = blk[X] * RT + xl;
+              if (x < No && y < No && z < No) {
+                const size_t i3 = y + (size_t)z * No + (size_t)x * NoNo;
+                Wt[pi * RTILE + xl + RS1 * l0 + RS2 * l1] += Ci[i3];
+                if (CT) Zt[pi * RTILE + xl + RS1 * l0 + RS2 * l1] += Zi[i3];
+              }
+            }
+          }
+        __syncthreads();
+        // ---- energy of the (i in I, j in J, k in K) points with k <= j <= i
+#pragma unroll
+        for (int it = 0; it < 2; it++) {
+          const int e = tid + REDUCE_THREADS * it;
+          const int il = e & 7, jl = (e >> 3) & 7, kl = e >> 6;
+          const int i = I * RT + il, j = J * RT + jl, k = K * RT + kl;
+          if (i < No && j <= i && k <= j) {
+            // tiles: 0 (I,J,K) 1 (I,K,J) 2 (J,I,K) 3 (J,K,I) 4 (K,I,J) 5 (K,J,I)
+            const int o0 = il + RS1 * jl + RS2 * kl, o1 = il + RS1 * kl + RS2 * jl;
+            const int o2 = RTILE * 2 + jl + RS1 * il + RS2 * kl, o3 = RTILE * 3 + jl + RS1 * kl + RS2 * il;
+            const int o4 = RTILE * 4 + kl + RS1 * il + RS2 * jl, o5 = RTILE * 5 + kl + RS1 * jl + RS2 * il;
+            const double A = Wt[o0], B = Wt[RTILE + o1], C = Wt[o2], D = Wt[o3], E = Wt[o4], F = Wt[o5];
+            // Vabij entries; pair blocks: 0 (I,J) 1 (I,K) 2 (J,I) 3 (J,K) 4 (K,I) 5 (K,J)
+            const int pij = 0 * 64 + il + 8 * jl, pik = 1 * 64 + il + 8 * kl, pji = 2 * 64 + jl + 8 * il;
+            const int pjk = 3 * 64 + jl + 8 * kl, pki = 4 * 64 + kl + 8 * il, pkj = 5 * 64 + kl + 8 * jl;
+            const double *Vbc = Vb, *Vac = Vb + 384, *Vab = Vb + 768;
+            const double tai = sTa[i], taj = sTa[j], tak = sTa[k];
+            const double tbi = sTb[i], tbj = sTb[j], tbk = sTb[k];
+            const double tci = sTc[i], tcj = sTc[j], tck = sTc[k];
+            // Z[x,y,z] = T[x,y,z] + Tai[a,x] Vbc[y,z] + Tai[b,y] Vac[x,z] + Tai[c,z] Vab[x,y]
+            // (Equations.cxx:420-422, three separate += in this order)
+            double U = Zt[o0], V = Zt[RTILE + o1], W = Zt[o2], X = Zt[o3], Y = Zt[o4], Z = Zt[o5];
+            U = ((U + tai * Vbc[pjk]) + tbj * Vac[pik]) + tck * Vab[pij];  // Z[i,j,k]
+            V = ((V + tai * Vbc[pkj]) + tbk * Vac[pij]) + tcj * Vab[pik];  // Z[i,k,j]
+            W = ((W + taj * Vbc[pik]) + tbi * Vac[pjk]) + tck * Vab[pji];  // Z[j,i,k]
+            X = ((X + taj * Vbc[pki]) + tbk * Vac[pji]) + tci * Vab[pjk];  // Z[j,k,i]
+            Y = ((Y + tak * Vbc[pij]) + tbi * Vac[pkj]) + tcj * Vab[pki];  // Z[k,i,j]
+            Z = ((Z + tak * Vbc[pji]) + tbj * Vac[pki]) + tci * Vab[pkj];  // Z[k,j,i]
+            const double facjk = (j == k) ? 0.5 : 1.0, facij = (i == j) ? 0.5 : 1.0;
+            const double den = epsabc - ((sEps[i] + sEps[j]) + sEps[k]);
+            double value;
+            if (!same) {  // get_energy_distinct, Equations.cxx:129-166
+              const double UXY = U + (X + Y), VWZ = V + (W + Z);
+              const double ADE = A + (D + E), BCF = B + (C + F);
+              const double first = A * U + (B * V + (C * W + (D * X + (E * Y + F * Z))));
+              const double second = (UXY - 2.0 * VWZ) * ADE;
+              const double third = (VWZ - 2.0 * UXY) * BCF;
+              value = 3.0 * first + (second + third);
+            } else {  // get_energy_same, Equations.cxx:209-226: cyclic permutations only
+              const double ABC = A + (D + E), UVW = U + (X + Y);
+              value = 3.0 * ((A * U + D * X) + E * Y) - ABC * UVW;
+            }
+            esum += ((2.0 * value) / den) * (facjk * facij);
+          }
+        }
+      }
+
+  // block reduction in a fixed order
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) esum += __shfl_down_sync(0xffffffffu, esum, off);
+  __syncthreads();
+  if ((tid & 31) == 0) sRed[tid >> 5] = esum;
+  __syncthreads();
+  if (tid == 0) {
+    double s = 0.0;
+    for (int w = 0; w < REDUCE_THREADS / 32; w++) s += sRed[w];
+    P.e_tuple[tup] = s;
+  }
+}
+
+// total[0] += sum_t e_tuple[t] in a fixed order (one CTA); keeps the energy on the device
+__global__ void __launch_bounds__(256) accumulate_kernel(const double *e_tuple, int n, double *total) {
+  __shared__ double s[256];
+  double v = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) v += e_tuple[i];
+  s[threadIdx.x] = v;
+  __syncthreads();
+  for (int off = 128; off > 0; off >>= 1) {
+    if ((int)threadIdx.x < off) s[threadIdx.x] += s[threadIdx.x + off];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) total[0] += s[0];
+}
+
+// debug / parity only: materialise the reference's Tijk and Zijk for one tuple of the batch
+__global__ void cubes_kernel(const ReduceParams P, int tup, double *Tijk, double *Zijk) {
+  const int No = P.No, Nv = P.Nv;
+  const size_t NoNo = (size_t)No * No, cube = NoNo * No;
+  const int4 abc = P.tuples[tup];
+  const double *Ck = P.R + (size_t)tup * 3 * cube, *Cj = Ck + cube, *Ci = Cj + cube;
+  const double *Vbc = P.VIJ + (size_t)P.vtab[abc.y + abc.z * Nv] * NoNo;
+  const double *Vac = P.VIJ + (size_t)P.vtab[abc.x + abc.z * Nv] * NoNo;
+  const double *Vab = P.VIJ + (size_t)P.vtab[abc.x + abc.y * Nv] * NoNo;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < cube; e += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(e % No), j = (int)((e / No) % No), k = (int)(e / NoNo);
+    const double w = (Ck[i + (size_t)j * No + (size_t)k * NoNo] + Cj[i + (size_t)k * No + (size_t)j * NoNo]) +
+                     Ci[j + (size_t)k * No + (size_t)i * NoNo];
+    if (Tijk) Tijk[e] = w;
+    if (Zijk)
+      Zijk[e] = ((w + P.Tai[abc.x + (size_t)i * Nv] * Vbc[j + (size_t)k * No]) +
+                 P.Tai[abc.y + (size_t)j * Nv] * Vac[i + (size_t)k * No]) +
+                P.Tai[abc.z + (size_t)k * Nv] * Vab[i + (size_t)j * No];
+  }
+}
+
+}  // namespace ab

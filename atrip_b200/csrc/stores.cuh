@@ -1,0 +1,208 @@
+// HBM stores of the engine and the kernels that build them.
+//
+// The reference keeps five "slice unions" per rank (Unions.hpp:77-278) in the layouts CTF::slice
+// produces.  Here the slices are stored in the layout the contraction kernel's TMA tensor maps
+// read directly (DESIGN.md "Data layout"):
+//   AX [xslot][m = p + q No][Kp]   kappa <  Nv      : T_x[E,p,q]  = Tabij[x,E,p,q]     (TAPHH)
+//                                  Nv <= kappa < Nv+No: -H_x[q,p,L] = -Vijka[q,p,L,x]   (HHHA)
+//                                  rest               : 0
+//   BY [bslot][r][Kp]              kappa <  Nv      : V_yz[E,r]   = Vabci[y,z,E,r]     (ABPH)
+//                                  hole part, slot (y,z), y<z or "normal" diagonal:
+//                                                     Tabij[y,z,L,r]                    (TABHH)
+//                                  hole part, slot (y,z), y>z or "transposed" diagonal:
+//                                                     Tabij[z,y,r,L]
+//   VIJ[vslot][i + j No]           Vabij[y,z,i,j]                                       (ABHH)
+// Slots are looked up through int tables (xtab, btab, vtab) so that a rank that stores only its
+// own slices plus a fetch cache uses the same kernels as a rank that stores everything.
+#pragma once
+#include "common.cuh"
+
+namespace ab {
+
+struct StoreDims {
+  int No, Nv, Kp;
+};
+
+// ------------------------------------------------------------------ synthetic fill (device)
+// one thread per store element; the source tensor's column-major linear index is rebuilt and
+// hashed, so the stores hold exactly what ingesting oracle_fill()ed host tensors would give.
+__global__ void fill_AX_kernel(double *AX, StoreDims d, const int *xlist, int nx, uint64_t keyT, uint64_t keyH,
+                               double scale) {
+  const size_t per = (size_t)d.No * d.No * d.Kp, total = per * nx;
+  const size_t Nv = d.Nv, No = d.No;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const size_t s = e / per, r = e - s * per;
+    const size_t m = r / d.Kp, kap = r - m * d.Kp;
+    const size_t p = m % No, q = m / No, x = xlist[s];
+    double v = 0.0;
+    if (kap < Nv) v = synth_val(keyT, x + kap * Nv + p * Nv * Nv + q * Nv * Nv * No, scale);
+    else if (kap < Nv + No) {
+      const size_t L = kap - Nv;
+      v = -synth_val(keyH, q + p * No + L * No * No + x * No * No * No, scale);
+    }
+    AX[e] = v;
+  }
+}
+
+// slot s holds ordered pair (ylist[s], zlist[s]); tflag[s] != 0 marks the transposed diagonal
+__global__ void fill_BY_kernel(double *BY, StoreDims d, const int *ylist, const int *zlist, const int *tflag,
+                               size_t nb, uint64_t keyV, uint64_t keyT, double scale) {
+  const size_t per = (size_t)d.No * d.Kp, total = per * nb;
+  const size_t Nv = d.Nv, No = d.No;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const size_t s = e / per, rr = e - s * per;
+    const size_t r = rr / d.Kp, kap = rr - r * d.Kp;
+    const size_t y = ylist[s], z = zlist[s];
+    double v = 0.0;
+    if (kap < Nv) v = synth_val(keyV, y + z * Nv + kap * Nv * Nv + r * Nv * Nv * Nv, scale);
+    else if (kap < Nv + No) {
+      const size_t L = kap - Nv;
+      const bool transposed = (y > z) || (y == z && tflag[s]);
+      v = transposed ? synth_val(keyT, z + y * Nv + r * Nv * Nv + L * Nv * Nv * No, scale)
+                     : synth_val(keyT, y + z * Nv + L * Nv * Nv + r * Nv * Nv * No, scale);
+    }
+    BY[e] = v;
+  }
+}
+
+__global__ void fill_VIJ_kernel(double *VIJ, StoreDims d, const int *ylist, const int *zlist, size_t nv,
+                                uint64_t key, double scale) {
+  const size_t per = (size_t)d.No * d.No, total = per * nv;
+  const size_t Nv = d.Nv, No = d.No;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const size_t s = e / per, r = e - s * per;
+    const size_t i = r % No, j = r / No;
+    VIJ[e] = synth_val(key, (size_t)ylist[s] + (size_t)zlist[s] * Nv + i * Nv * Nv + j * Nv * Nv * No, scale);
+  }
+}
+
+__global__ void fill_small_kernel(double *eps_i, double *eps_a, double *Tai, StoreDims d, uint64_t kI, uint64_t kA,
+                                  uint64_t kT, double scale) {
+  const size_t n = (size_t)d.No + d.Nv + (size_t)d.No * d.Nv;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+    if (e < (size_t)d.No) eps_i[e] = __dadd_rn(-2.0, __dmul_rn(1.5, synth_u(kI, e)));
+    else if (e < (size_t)d.No + d.Nv) eps_a[e - d.No] = __dadd_rn(0.5, __dmul_rn(3.5, synth_u(kA, e - d.No)));
+    else Tai[e - d.No - d.Nv] = synth_val(kT, e - d.No - d.Nv, scale);
+  }
+}
+
+// ------------------------------------------------------------------ ingest from host tensors
+// Each kernel consumes one contiguous chunk of a CTF-layout tensor that was copied to the device
+// and scatters it into the stores.  *_tab < 0 means "this rank does not store that slice".
+
+// chunk = Tabij[:, :, p, q] (Nv x Nv, alpha fastest).  Writes
+//   AX[xtab[alpha]][p + q No][beta]                       (TAPHH, Unions.hpp:77-113)
+//   BY[btab[alpha + beta Nv]][q][Nv + p]         alpha <= beta   (TABHH normal,  Unions.hpp:239-278)
+//   BY[btab[beta + alpha Nv] or diagT][p][Nv + q] alpha <= beta   (TABHH transposed)
+__global__ void ingest_Tabij_kernel(const double *chunk, StoreDims d, int p, int q, double *AX, const int *xtab,
+                                    double *BY, const int *btab) {
+  __shared__ double tile[32][33];
+  const int Nv = d.Nv, No = d.No;
+  const size_t Kp = d.Kp;
+  const int a0 = blockIdx.x * 32, b0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int al = a0 + threadIdx.x, be = b0 + r;
+    double v = 0.0;
+    if (al < Nv && be < Nv) {
+      v = chunk[al + (size_t)be * Nv];
+      if (al <= be) {
+        const int s1 = btab[al + be * Nv];
+        if (s1 >= 0) BY[((size_t)s1 * No + q) * Kp + Nv + p] = v;
+        const int s2 = btab[al == be ? Nv * Nv + al : be + al * Nv];
+        if (s2 >= 0) BY[((size_t)s2 * No + p) * Kp + Nv + q] = v;
+      }
+    }
+    tile[r][threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int al = a0 + r, be = b0 + threadIdx.x;
+    if (al < Nv && be < Nv) {
+      const int s = xtab[al];
+      if (s >= 0) AX[((size_t)s * No * No + p + (size_t)q * No) * Kp + be] = tile[threadIdx.x][r];
+    }
+  }
+}
+
+// chunk = Vijka[:, :, :, x0 .. x0+nx) (No^3 per x).  AX[xtab[x]][p + q No][Nv + L] = -Vijka[q,p,L,x]
+// (HHHA, Unions.hpp:115-152; sign and (p,q) swap folded in here, see contraction.cuh)
+__global__ void ingest_Vijka_kernel(const double *chunk, StoreDims d, int x0, int nx, double *AX, const int *xtab) {
+  const size_t No = d.No, cube = No * No * No, total = cube * nx;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const size_t xs = e / cube, r = e - xs * cube;
+    // enumerate destination-friendly: L fastest
+    const size_t L = r % No, m = r / No, p = m % No, q = m / No;
+    const int s = xtab[x0 + xs];
+    if (s >= 0) AX[((size_t)s * No * No + m) * d.Kp + d.Nv + L] = -chunk[xs * cube + q + p * No + L * No * No];
+  }
+}
+
+// chunk = Vabij[:, :, i, j] (Nv x Nv).  VIJ[vtab[y + z Nv]][i + j No]   (ABHH, Unions.hpp:199-237)
+__global__ void ingest_Vabij_kernel(const double *chunk, StoreDims d, int i, int j, double *VIJ, const int *vtab) {
+  const size_t n = (size_t)d.Nv * d.Nv;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+    const int s = vtab[e];
+    if (s >= 0) VIJ[(size_t)s * d.No * d.No + i + (size_t)j * d.No] = chunk[e];
+  }
+}
+
+// chunk = Vabci[:, :, E0 .. E0+ne, r] (ne x Nv^2, pair index fastest).  BY[btab[pair]][r][E0 + e]
+// and the transposed-diagonal twin of (y,y)   (ABPH, Unions.hpp:154-197)
+__global__ void ingest_Vabci_kernel(const double *chunk, StoreDims d, int E0, int ne, int r, double *BY,
+                                    const int *btab) {
+  __shared__ double tile[16][33];
+  const size_t NvNv = (size_t)d.Nv * d.Nv;
+  const size_t pr0 = (size_t)blockIdx.x * 32;
+  // load: threadIdx.x runs along the pair index (coalesced), threadIdx.y along E
+  for (int e = threadIdx.y; e < 16; e += blockDim.y) {
+    const size_t pr = pr0 + threadIdx.x;
+    tile[e][threadIdx.x] = (e < ne && pr < NvNv) ? chunk[(size_t)e * NvNv + pr] : 0.0;
+  }
+  __syncthreads();
+  // store: 16 consecutive E per pair
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  for (int w = tid; w < 32 * 16; w += blockDim.x * blockDim.y) {
+    const int e = w & 15, pl = w >> 4;
+    const size_t pr = pr0 + pl;
+    if (pr < NvNv && e < ne) {
+      const int s = btab[pr];
+      const double v = tile[e][pl];
+      if (s >= 0) BY[((size_t)s * d.No + r) * d.Kp + E0 + e] = v;
+      const int y = (int)(pr % d.Nv), z = (int)(pr / d.Nv);
+      if (y == z) {
+        const int s2 = btab[NvNv + y];
+        if (s2 >= 0) BY[((size_t)s2 * d.No + r) * d.Kp + E0 + e] = v;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ read back in reference layout
+// kind: 100 TA(x), 101 VIJKA(x), 200 VABCI(x,y), 201 TABIJ(x,y), 202 VABIJ(x,y)
+__global__ void read_slice_kernel(int kind, StoreDims d, const double *AXx, const double *BYxy, const double *VIJxy,
+                                  int y, double *out) {
+  const size_t No = d.No, Nv = d.Nv, Kp = d.Kp;
+  size_t n = 0;
+  if (kind == 100) n = Nv * No * No;
+  else if (kind == 101) n = No * No * No;
+  else if (kind == 200) n = Nv * No;
+  else n = No * No;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+    if (kind == 100) {  // TX[E + p Nv + q Nv No]
+      const size_t E = e % Nv, m = e / Nv;
+      out[e] = AXx[m * Kp + E];
+    } else if (kind == 101) {  // HX[p + q No + L No^2] = -AX[(q + p No)][Nv + L]
+      const size_t p = e % No, q = (e / No) % No, L = e / (No * No);
+      out[e] = -AXx[(q + p * No) * Kp + Nv + L];
+    } else if (kind == 200) {  // VXY[E + r Nv]
+      const size_t E = e % Nv, r = e / Nv;
+      out[e] = BYxy[r * Kp + E];
+    } else if (kind == 201) {  // TXY[p + q No] = T_x[E = y, p, q]
+      out[e] = AXx[e * Kp + y];
+    } else {
+      out[e] = VIJxy[e];
+    }
+  }
+}
+
+}  // namespace ab
