@@ -20,6 +20,8 @@ SYMBOLS = [
     "atrip_b200_fill_synthetic", "atrip_b200_build_tuples", "atrip_b200_set_tuples",
     "atrip_b200_num_tuples", "atrip_b200_get_tuples", "atrip_b200_run", "atrip_b200_tuple_debug",
     "atrip_b200_read_slice", "atrip_b200_last_timing", "atrip_b200_kp", "atrip_b200_flops_per_tuple",
+    "atrip_b200_host_tuples", "atrip_b200_host_slice_owner", "atrip_b200_measure_dmma_peak",
+    "atrip_b200_synth_to_host", "atrip_b200_batch_tuples",
 ]
 
 NAIVE, GROUP_AND_SORT = 0, 1
@@ -81,10 +83,49 @@ def load_library():
     L.atrip_b200_last_timing.argtypes = [ctx, _dp]
     L.atrip_b200_kp.argtypes = [ctx]
     L.atrip_b200_kp.restype = C.c_int64
+    L.atrip_b200_batch_tuples.argtypes = [ctx]
+    L.atrip_b200_batch_tuples.restype = C.c_int64
     L.atrip_b200_flops_per_tuple.argtypes = [ctx]
     L.atrip_b200_flops_per_tuple.restype = C.c_double
+    L.atrip_b200_host_tuples.argtypes = [C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _up, C.c_int64]
+    L.atrip_b200_host_tuples.restype = C.c_int64
+    L.atrip_b200_host_slice_owner.argtypes = [C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int32]
+    L.atrip_b200_host_slice_owner.restype = C.c_int32
+    L.atrip_b200_measure_dmma_peak.argtypes = [C.c_int32, _dp]
+    L.atrip_b200_synth_to_host.argtypes = [C.c_int32, C.c_uint64, C.c_int32, C.c_double, C.c_uint64, C.c_uint64, _dp]
     _lib = L
     return L
+
+
+def measure_dmma_peak(device=0):
+    """FP64 tensor-core ceiling of the device in TFLOP/s (register-resident DMMA loop)"""
+    L = load_library()
+    v = C.c_double(0)
+    if L.atrip_b200_measure_dmma_peak(device, C.byref(v)) != 0:
+        raise EngineError(L.atrip_b200_last_error().decode())
+    return v.value
+
+
+def synth_to_host(device, seed, tensor_id, scale, first, count, host):
+    """fill host[0:count] (numpy array or int address) with the synthetic tensor values"""
+    L = load_library()
+    if L.atrip_b200_synth_to_host(device, seed, tensor_id, scale, first, count, _ptr(host)) != 0:
+        raise EngineError(L.atrip_b200_last_error().decode())
+
+
+def host_tuples(distribution, Nv, rank=0, nranks=1, pad=True):
+    """tuple list of one rank, computed on the host by the library (no GPU needed)"""
+    L = load_library()
+    n = L.atrip_b200_host_tuples(distribution, Nv, rank, nranks, int(pad), None, 0)
+    if n < 0:
+        raise EngineError(L.atrip_b200_last_error().decode())
+    out = np.empty((n, 3), dtype=np.uint64)
+    L.atrip_b200_host_tuples(distribution, Nv, rank, nranks, int(pad), out.ctypes.data_as(_up), n)
+    return out
+
+
+def slice_owner(kind, x, y, Nv, nranks):
+    return load_library().atrip_b200_host_slice_owner(kind, x, y, Nv, nranks)
 
 
 def _ptr(a):
@@ -201,6 +242,10 @@ class Engine:
     @property
     def kp(self):
         return self.L.atrip_b200_kp(self.ctx)
+
+    @property
+    def batch_tuples(self):
+        return self.L.atrip_b200_batch_tuples(self.ctx)
 
     @property
     def flops_per_tuple(self):

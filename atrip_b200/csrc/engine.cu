@@ -650,6 +650,32 @@ void read_slice_impl(atrip_b200_ctx *c, int kind, int64_t x, int64_t y, double *
   cudaFree(d);
 }
 
+// register-resident DMMA loop: the FP64 tensor ceiling (same loop as tools/fp64_peak.cu)
+__global__ void dmma_peak_kernel(double *out, int iters) {
+  double acc[16][2];
+#pragma unroll
+  for (int i = 0; i < 16; i++) acc[i][0] = acc[i][1] = 0.0;
+  const double a = threadIdx.x * 1e-3, b = threadIdx.x * 2e-3;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < 16; i++) dmma884(acc[i][0], acc[i][1], a, b);
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 16; i++) s += acc[i][0] + acc[i][1];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+__global__ void synth_range_kernel(double *out, uint64_t key, int tensor_id, double scale, uint64_t first,
+                                   uint64_t count) {
+  for (uint64_t e = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; e < count; e += (uint64_t)gridDim.x * blockDim.x) {
+    const double u = synth_u(key, first + e);
+    out[e] = tensor_id == T_EPS_I   ? __dadd_rn(-2.0, __dmul_rn(1.5, u))
+             : tensor_id == T_EPS_A ? __dadd_rn(0.5, __dmul_rn(3.5, u))
+                                    : __dmul_rn(scale, __dadd_rn(u, -0.5));
+  }
+}
+
 template <typename F>
 int guarded(atrip_b200_ctx *c, F f) {
   try {
@@ -771,9 +797,76 @@ int atrip_b200_last_timing(const atrip_b200_ctx *c, double *out6) {
   return 0;
 }
 int64_t atrip_b200_kp(const atrip_b200_ctx *c) { return c->Kp; }
+int64_t atrip_b200_batch_tuples(const atrip_b200_ctx *c) { return c->batch; }
 double atrip_b200_flops_per_tuple(const atrip_b200_ctx *c) {
   const double No = c->No, Nv = c->Nv;
   return 12.0 * No * No * No * (No + Nv);
+}
+
+int atrip_b200_measure_dmma_peak(int32_t device, double *tflops) {
+  return guarded(nullptr, [&] {
+    CUDA_OK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_OK(cudaGetDeviceProperties(&prop, device));
+    const int grid = prop.multiProcessorCount * 2, threads = 256, iters = 40000;
+    double *out = dalloc<double>((size_t)grid * threads);
+    cudaEvent_t e0, e1;
+    CUDA_OK(cudaEventCreate(&e0));
+    CUDA_OK(cudaEventCreate(&e1));
+    double best = 0;
+    for (int rep = 0; rep < 4; rep++) {
+      CUDA_OK(cudaEventRecord(e0));
+      dmma_peak_kernel<<<grid, threads>>>(out, iters);
+      CUDA_OK(cudaEventRecord(e1));
+      CUDA_OK(cudaEventSynchronize(e1));
+      float ms = 0;
+      CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+      const double tf = (double)grid * (threads / 32) * iters * 16 * 512.0 / (ms * 1e-3) / 1e12;
+      if (rep > 0) best = std::max(best, tf);
+    }
+    CUDA_OK(cudaGetLastError());
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    *tflops = best;
+  });
+}
+
+int atrip_b200_synth_to_host(int32_t device, uint64_t seed, int32_t tensor_id, double scale, uint64_t first,
+                             uint64_t count, double *host) {
+  return guarded(nullptr, [&] {
+    CUDA_OK(cudaSetDevice(device));
+    const uint64_t chunk = 1ull << 26;  // 512 MiB
+    double *d = dalloc<double>(std::min<uint64_t>(chunk, std::max<uint64_t>(count, 1)));
+    for (uint64_t off = 0; off < count; off += chunk) {
+      const uint64_t n = std::min(chunk, count - off);
+      synth_range_kernel<<<2048, 256>>>(d, synth_key(seed, tensor_id), tensor_id, scale, first + off, n);
+      CUDA_OK(cudaGetLastError());
+      CUDA_OK(cudaMemcpy(host + off, d, n * sizeof(double), cudaMemcpyDeviceToHost));
+    }
+    cudaFree(d);
+  });
+}
+
+int64_t atrip_b200_host_tuples(int32_t distribution, int64_t Nv, int32_t rank, int32_t nranks, int32_t pad,
+                               uint64_t *abc, int64_t cap) {
+  if (Nv < 1 || nranks < 1 || rank < 0 || rank >= nranks || (distribution != 0 && distribution != 1)) {
+    g_error = "atrip_b200_host_tuples: bad arguments";
+    return -1;
+  }
+  std::vector<Tuple> t = distribution == 0 ? naive_tuples(Nv, rank, nranks)
+                                           : group_and_sort_tuples(Nv, rank, nranks, pad != 0);
+  if (distribution == 0 && !pad)
+    while (!t.empty() && t.back() == Tuple{0, 0, 0}) t.pop_back();
+  const int64_t n = (int64_t)t.size();
+  for (int64_t i = 0; i < n && i < cap; i++)
+    for (int d = 0; d < 3; d++) abc[3 * i + d] = t[i][d];
+  return n;
+}
+
+int32_t atrip_b200_host_slice_owner(int32_t kind, int64_t x, int64_t y, int64_t Nv, int32_t nranks) {
+  if (kind == 100 || kind == 101) return (int32_t)(x % nranks);
+  return (int32_t)((x + y * Nv) % nranks);
 }
 
 }  // extern "C"

@@ -103,6 +103,29 @@ int atrip_b200_last_timing(const atrip_b200_ctx *ctx, double *out6);
 /* ---- derived constants the caller needs for reporting */
 int64_t atrip_b200_kp(const atrip_b200_ctx *ctx);            /* padded contraction length */
 double atrip_b200_flops_per_tuple(const atrip_b200_ctx *ctx); /* 12 No^3 (No+Nv), Atrip.cxx:578-580 */
+int64_t atrip_b200_batch_tuples(const atrip_b200_ctx *ctx);  /* tuples per contraction launch */
+
+/* ---- measurement helpers
+ *      FP64 tensor-core ceiling of the device, measured live with a register-resident
+ *      DMMA.8x8x4 loop (about 0.2 s); the roofline denominator of the contraction kernel
+ *      (MEASURED_PEAKS.json carries no FP64 figure).  Returns TFLOP/s in *tflops. */
+int atrip_b200_measure_dmma_peak(int32_t device, double *tflops);
+/*      counter-based synthetic values of one input tensor in CTF (column-major) order,
+ *      elements [first, first+count), generated on the device and copied to host memory;
+ *      lets a caller build host tensors of bench size without a multi-minute CPU fill.
+ *      tensor_id: 0 eps_i, 1 eps_a, 2 Tai, 3 Tabij, 4 Vabij, 5 Vijka, 6 Vabci, 7 Jijka, 8 Jabci */
+int atrip_b200_synth_to_host(int32_t device, uint64_t seed, int32_t tensor_id, double scale, uint64_t first,
+                             uint64_t count, double *host);
+
+/* ---- host-only utilities (no device needed; usable before any context exists)
+ *      tuple list of rank `rank` of `nranks` (3 x uint64 per tuple, padded with the fake tuple
+ *      when pad != 0); returns the list length, writes at most cap tuples.
+ *      distribution as in atrip_b200_build_tuples. */
+int64_t atrip_b200_host_tuples(int32_t distribution, int64_t Nv, int32_t rank, int32_t nranks, int32_t pad,
+                               uint64_t *abc, int64_t cap);
+/*      owner rank of a slice (replaces RankMap<F>::find, RankMap.cxx:35-85, one rank per node):
+ *      kind 100/101 -> x % nranks; pair kinds -> (x + y Nv) % nranks (RankMap.cxx:43-44) */
+int32_t atrip_b200_host_slice_owner(int32_t kind, int64_t x, int64_t y, int64_t Nv, int32_t nranks);
 
 #ifdef __cplusplus
 }

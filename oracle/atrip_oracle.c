@@ -84,6 +84,39 @@ void oracle_slice_ABHH(long No, long Nv, const double *Vabij, long x, long y, do
       out[p + q * No] = Vabij[x + y * Nv + p * Nv * Nv + q * Nv * Nv * No];
 }
 
+/* The 18 slices of one tuple straight from the counter-based generator, without the full
+ * tensors (which are 25 GB at the bench size): same element <-> source-index maps as the
+ * oracle_slice_* functions above.  out[] order = reference argument order of
+ * doubles_contribution (Equations.hpp:64-96) followed by VABij, VACij, VBCij:
+ * VAB VAC VBC VBA VCA VCB | HA HB HC | TA TB TC | TAB TAC TBC | VABij VACij VBCij */
+void oracle_synth_tuple_slices(uint64_t seed, double scale, long No, long Nv, long a,
+                               long b, long c, double **out) {
+  const long abc[3] = {a, b, c};
+  const long ph[6][2] = {{a, b}, {a, c}, {b, c}, {b, a}, {c, a}, {c, b}};
+  const long hh[3][2] = {{a, b}, {a, c}, {b, c}};
+  const uint64_t uNv = (uint64_t)Nv, uNo = (uint64_t)No;
+  for (int s = 0; s < 6; s++)
+    for (uint64_t r = 0; r < uNo; r++)
+      for (uint64_t E = 0; E < uNv; E++)
+        out[s][E + r * uNv] = oracle_synth(seed, ORACLE_VABCI,
+            (uint64_t)ph[s][0] + (uint64_t)ph[s][1] * uNv + E * uNv * uNv + r * uNv * uNv * uNv, scale);
+  for (int s = 0; s < 3; s++)
+    oracle_fill(seed, ORACLE_VIJKA, scale, (uint64_t)abc[s] * uNo * uNo * uNo, uNo * uNo * uNo, out[6 + s]);
+  for (int s = 0; s < 3; s++)
+    for (uint64_t q = 0; q < uNo; q++)
+      for (uint64_t p = 0; p < uNo; p++)
+        for (uint64_t E = 0; E < uNv; E++)
+          out[9 + s][E + p * uNv + q * uNv * uNo] = oracle_synth(seed, ORACLE_TABIJ,
+              (uint64_t)abc[s] + E * uNv + p * uNv * uNv + q * uNv * uNv * uNo, scale);
+  for (int s = 0; s < 3; s++)
+    for (uint64_t q = 0; q < uNo; q++)
+      for (uint64_t p = 0; p < uNo; p++) {
+        const uint64_t idx = (uint64_t)hh[s][0] + (uint64_t)hh[s][1] * uNv + p * uNv * uNv + q * uNv * uNv * uNo;
+        out[12 + s][p + q * uNo] = oracle_synth(seed, ORACLE_TABIJ, idx, scale);
+        out[15 + s][p + q * uNo] = oracle_synth(seed, ORACLE_VABIJ, idx, scale);
+      }
+}
+
 /* ------------------------------------------------------------- equations -- */
 /* doubles_contribution, Equations.cxx:455-728.  Stated term by term as the
  * reference's own element-wise form (Equations.cxx:687-726), which the dgemm

@@ -33,6 +33,10 @@ void oracle_slice_HHHA(long No, long Nv, const double *Vijka, long x, double *ou
 void oracle_slice_ABPH(long No, long Nv, const double *Vabci, long x, long y, double *out);
 void oracle_slice_ABHH(long No, long Nv, const double *Vabij, long x, long y, double *out);
 
+/* the 18 slices of one tuple from the generator alone (see atrip_oracle.c) */
+void oracle_synth_tuple_slices(uint64_t seed, double scale, long No, long Nv, long a,
+                               long b, long c, double **out);
+
 /* per-tuple math (reference Equations.cxx) */
 void oracle_doubles(long No, long Nv, const double *VAB, const double *VAC,
                     const double *VBC, const double *VBA, const double *VCA,

@@ -124,6 +124,18 @@ class Oracle:
             S[nm] = self.slice_ABHH(No, Nv, t[VABIJ], x, y)
         return S
 
+    SLICE_ORDER = ["VAB", "VAC", "VBC", "VBA", "VCA", "VCB", "HA", "HB", "HC", "TA", "TB", "TC",
+                   "TAB", "TAC", "TBC", "VABij", "VACij", "VBCij"]
+
+    def synth_tuple_slices(self, No, Nv, abc, seed=12345, scale=0.1):
+        """the 18 slices of one tuple straight from the generator (no full tensors needed)"""
+        sizes = [Nv * No] * 6 + [No ** 3] * 3 + [Nv * No * No] * 3 + [No * No] * 6
+        S = {k: np.empty(n) for k, n in zip(self.SLICE_ORDER, sizes)}
+        arr = (_dp * 18)(*[_d(S[k]) for k in self.SLICE_ORDER])
+        self.L.oracle_synth_tuple_slices(C.c_uint64(seed), C.c_double(scale), C.c_long(No), C.c_long(Nv),
+                                         C.c_long(abc[0]), C.c_long(abc[1]), C.c_long(abc[2]), arr)
+        return S
+
     # ---- equations
     DOUBLES_ORDER = ["VAB", "VAC", "VBC", "VBA", "VCA", "VCB", "HA", "HB", "HC",
                      "TA", "TB", "TC", "TAB", "TAC", "TBC"]

@@ -1,0 +1,216 @@
+"""GPU: the CUDA path through the C-ABI against (1) vectors produced by the reference itself
+(tests/golden/), (2) the oracle on the same seeded inputs, (3) size-independent properties at
+the bench sizes.  Tolerances follow BASELINE.json north_star: energy |dE| <= 1e-10 Eh and
+rel <= 1e-12 on inputs scaled to |E| = O(0.01..1); cubes 1e-13 relative to max|Tijk|."""
+import numpy as np
+import pytest
+
+from conftest import fh
+from oracle.oracle import EPS_A, EPS_I, JABCI, JIJKA, TABIJ, TAI, VABCI, VABIJ, VIJKA
+
+pytestmark = pytest.mark.gpu
+
+E_ABS, E_REL, CUBE_REL = 1e-10, 1e-12, 1e-13
+
+
+@pytest.fixture(scope="module")
+def ab():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import atrip_b200
+    from atrip_b200 import capi
+    assert capi.load_library() is not None
+    return atrip_b200
+
+
+def engine_from_host(ab, o, No, Nv, seed, scale, with_J=False, **kw):
+    t = o.inputs(No, Nv, seed=seed, scale=scale, with_J=with_J)
+    eng = ab.Engine(No, Nv, with_J=with_J, **kw)
+    eng.load_all(t[EPS_I], t[EPS_A], t[TAI], t[TABIJ], t[VABIJ], t[VIJKA], t[VABCI], t.get(JIJKA), t.get(JABCI))
+    return eng, t
+
+
+def close_energy(e, ref):
+    return abs(e - ref) <= E_ABS and abs(e - ref) <= E_REL * abs(ref)
+
+
+def test_runs_match_reference_vectors(ab, oracle, golden):
+    """whole Atrip::run energies of the reference (np=1, GROUP_AND_SORT), ingest path"""
+    from atrip_b200 import capi
+    for r in golden["runs"]:
+        eng, _ = engine_from_host(ab, oracle, r["No"], r["Nv"], r["seed"], r["scale"], with_J=r["with_J"])
+        eng.build_tuples(capi.GROUP_AND_SORT)
+        e, ct = eng.run()
+        assert close_energy(-e, fh(r["energy"])), (r, -e)
+        ref_ct = fh(r["ct_energy"])
+        assert abs(-ct - ref_ct) <= E_ABS and abs(-ct - ref_ct) <= 1e-11 * max(abs(ref_ct), abs(e)), (r, -ct)
+        eng.close()
+
+
+def test_runs_device_fill_equals_ingest(ab, oracle, golden):
+    """synthetic stores generated on the device give the same energies bit for bit"""
+    from atrip_b200 import capi
+    for r in golden["runs"][:4]:
+        eng, _ = engine_from_host(ab, oracle, r["No"], r["Nv"], r["seed"], r["scale"], with_J=r["with_J"])
+        eng.build_tuples(capi.GROUP_AND_SORT)
+        e1 = eng.run()
+        eng.close()
+        eng = ab.Engine(r["No"], r["Nv"], with_J=r["with_J"])
+        eng.fill_synthetic(r["seed"], r["scale"])
+        eng.build_tuples(capi.GROUP_AND_SORT)
+        assert eng.run() == e1
+        eng.close()
+
+
+def test_tuples_match_reference_vectors(ab, oracle, golden):
+    """per-tuple Tijk / Zijk / energy of the reference's doubles/singles/energy functions"""
+    for rec in golden["tuples"]:
+        No, Nv = rec["No"], rec["Nv"]
+        eng = ab.Engine(No, Nv)
+        eng.fill_synthetic(rec["seed"], rec["scale"])
+        idx = [0, 1, No, No * No, No ** 3 // 2, No ** 3 - 1]
+        for g in rec["tuples"]:
+            e, T, Z = eng.tuple_debug(*g["abc"])
+            tmax = fh(g["Tabsmax"])
+            assert abs(e - fh(g["energy"])) <= E_REL * abs(e), (rec["No"], g["abc"])
+            assert np.abs(T[idx] - [fh(x) for x in g["Tsample"]]).max() <= CUBE_REL * tmax
+            assert np.abs(Z[idx] - [fh(x) for x in g["Zsample"]]).max() <= CUBE_REL * tmax
+            assert abs(T.sum() - fh(g["Tsum"])) <= 1e-11 * tmax * No ** 1.5
+        eng.close()
+
+
+@pytest.mark.parametrize("No,Nv", [(4, 8), (8, 24), (10, 40), (13, 29), (16, 33), (33, 40), (40, 56), (64, 72),
+                                   (100, 104), (7, 120)])
+def test_cubes_and_energy_vs_oracle(ab, oracle, No, Nv):
+    """odd and even sizes, all kernel variants: element-wise cubes against the oracle"""
+    seed, scale = 1000 + No, 0.1
+    t = oracle.inputs(No, Nv, seed=seed, scale=scale)
+    eng = ab.Engine(No, Nv)
+    eng.fill_synthetic(seed, scale)
+    tuples = [(0, 1, 2), (0, 0, 1), (0, 1, 1), (Nv - 3, Nv - 2, Nv - 1), (0, Nv - 1, Nv - 1), (2, 2, Nv - 1),
+              (1, Nv // 2, Nv - 2)]
+    for abc in tuples:
+        e, _, T, Z = oracle.tuple_energy(No, Nv, t, abc, want_cubes=True)
+        ge, gT, gZ = eng.tuple_debug(*abc)
+        tmax = np.abs(T).max()
+        assert np.abs(gT - T).max() <= CUBE_REL * tmax, abc
+        assert np.abs(gZ - Z).max() <= CUBE_REL * max(tmax, np.abs(Z).max()), abc
+        assert abs(ge - e) <= E_REL * abs(e), abc
+    eng.close()
+
+
+def test_slices_bit_exact_fill_and_ingest(ab, oracle):
+    """stores hold exactly the reference's slices (Unions.hpp layouts), from either source"""
+    from atrip_b200 import capi
+    No, Nv, seed, scale = 6, 19, 5, 0.1
+    engI, t = engine_from_host(ab, oracle, No, Nv, seed, scale)
+    engF = ab.Engine(No, Nv)
+    engF.fill_synthetic(seed, scale)
+    for eng in (engI, engF):
+        for x in range(0, Nv, 3):
+            assert np.array_equal(eng.read_slice(capi.TA, x), oracle.slice_TA(No, Nv, t[TABIJ], x))
+            assert np.array_equal(eng.read_slice(capi.VIJKA, x), oracle.slice_HHHA(No, Nv, t[VIJKA], x))
+            for y in range(0, Nv, 4):
+                assert np.array_equal(eng.read_slice(capi.VABCI, x, y), oracle.slice_ABPH(No, Nv, t[VABCI], x, y))
+                assert np.array_equal(eng.read_slice(capi.TABIJ, x, y), oracle.slice_ABHH(No, Nv, t[TABIJ], x, y))
+                if x <= y:
+                    assert np.array_equal(eng.read_slice(capi.VABIJ, x, y), oracle.slice_ABHH(No, Nv, t[VABIJ], x, y))
+    engI.close()
+    engF.close()
+
+
+def test_explicit_tuple_lists_fakes_and_batches(ab, oracle):
+    """set_tuples with fake tuples interleaved, several batch sizes, sub-ranges: same sums"""
+    No, Nv, seed, scale = 9, 21, 8, 0.05
+    t = oracle.inputs(No, Nv, seed=seed, scale=scale)
+    allt = oracle.all_tuples(Nv)
+    sub = allt[::7]
+    with_fakes = np.concatenate([sub[:50], np.zeros((5, 3), np.uint64), sub[50:], np.zeros((3, 3), np.uint64)])
+    want, _ = oracle.run(No, Nv, t, tuples=sub)
+    got = []
+    for batch in (0, 1, 37, 4096):
+        eng = ab.Engine(No, Nv, batch_tuples=batch)
+        eng.fill_synthetic(seed, scale)
+        eng.set_tuples(with_fakes)
+        e, _ = eng.run()
+        assert close_energy(-e, want)
+        assert eng.last_timing()["tuples"] == len(sub)  # fakes are skipped, not counted
+        n = eng.num_tuples()
+        e1, _ = eng.run(0, n // 3)
+        e2, _ = eng.run(n // 3, n - n // 3)
+        assert abs((e1 + e2) - e) <= 1e-13 * abs(e)
+        got.append(e)
+        eng.close()
+    assert max(got) - min(got) <= 1e-13 * abs(got[0])
+    # empty range and empty list
+    eng = ab.Engine(No, Nv)
+    eng.fill_synthetic(seed, scale)
+    eng.set_tuples(np.zeros((0, 3), np.uint64))
+    assert eng.run() == (0.0, 0.0)
+    eng.close()
+
+
+def test_group_and_sort_shards_sum_to_total(ab, oracle):
+    """multi-GPU sharding logic on one device: the per-rank lists of a 4-GPU job, run one after
+    the other, add up to the single-rank energy (the final allreduce is a plain sum)"""
+    from atrip_b200 import capi
+    No, Nv, seed, scale = 8, 22, 77, 0.05
+    t = oracle.inputs(No, Nv, seed=seed, scale=scale)
+    want, _ = oracle.run(No, Nv, t)
+    total = 0.0
+    for r in range(4):
+        eng = ab.Engine(No, Nv, rank=r, nranks=4)
+        eng.fill_synthetic(seed, scale)
+        eng.build_tuples(capi.GROUP_AND_SORT)
+        e, _ = eng.run()
+        total += e
+        eng.close()
+    assert close_energy(-total, want)
+
+
+def test_determinism_and_bench_size_properties(ab):
+    """bench-size (No=40, Nv=400) slice of tuples: run-to-run bit reproducibility, additivity over
+    sub-ranges and invariance to the batch size -- properties that need no CPU reference"""
+    from atrip_b200 import capi
+    No, Nv = 40, 400
+    eng = ab.Engine(No, Nv)
+    eng.fill_synthetic(12345, 0.01)
+    n = eng.build_tuples(capi.GROUP_AND_SORT)
+    assert n == Nv * (Nv + 1) * (Nv + 2) // 6 - Nv
+    first, count = n // 2, 3000
+    e1 = eng.run(first, count)
+    e2 = eng.run(first, count)
+    assert e1 == e2 and np.isfinite(e1[0]) and e1[0] != 0.0
+    ea = eng.run(first, 1000)[0] + eng.run(first + 1000, 2000)[0]
+    assert abs(ea - e1[0]) <= 1e-12 * abs(e1[0])
+    tup = eng.get_tuples()[first:first + count]
+    eng.close()
+    eng = ab.Engine(No, Nv, batch_tuples=250)
+    eng.fill_synthetic(12345, 0.01)
+    eng.set_tuples(tup)
+    assert abs(eng.run()[0] - e1[0]) <= 1e-12 * abs(e1[0])
+    eng.close()
+
+
+def test_bench_size_tuples_vs_oracle(ab, oracle):
+    """a few tuples at the bench size against the oracle's per-tuple path fed slice by slice
+    (the full tensors would be 25 GB on the host: the oracle is given synthetic slices)"""
+    No, Nv, seed, scale = 40, 400, 12345, 0.1
+    eng = ab.Engine(No, Nv)
+    eng.fill_synthetic(seed, scale)
+    epsi, epsa = oracle.fill(seed, EPS_I, scale, No), oracle.fill(seed, EPS_A, scale, Nv)
+    tai = oracle.fill(seed, TAI, scale, No * Nv)
+
+    for abc in [(3, 57, 399), (11, 11, 200)]:
+        a, b, c = abc
+        S = oracle.synth_tuple_slices(No, Nv, abc, seed=seed, scale=scale)
+        T = oracle.doubles(No, Nv, S)
+        Z = oracle.singles(No, Nv, abc, tai, S, T)
+        eps = float(epsa[a] + epsa[b] + epsa[c])
+        same = (a == b) != (b == c)
+        e = (oracle.energy_same if same else oracle.energy_distinct)(eps, No, epsi, T, Z)
+        ge, gT, gZ = eng.tuple_debug(*abc)
+        assert np.abs(gT - T).max() <= CUBE_REL * np.abs(T).max()
+        assert np.abs(gZ - Z).max() <= CUBE_REL * np.abs(Z).max()
+        assert abs(ge - e) <= E_REL * abs(e)
+    eng.close()

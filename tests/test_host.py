@@ -1,0 +1,80 @@
+"""CPU: host-side logic of the product and the shape of its C-ABI (no compute calls)."""
+import hashlib
+import os
+import re
+
+import numpy as np
+
+from atrip_b200 import capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(lib):
+    hdr = open(os.path.join(ROOT, "include", "atrip_b200.h")).read()
+    declared = set(re.findall(r"\b(atrip_b200_[a-zA-Z0-9_]+)\s*\(", hdr))
+    declared -= {"atrip_b200_ctx", "atrip_b200_config"}
+    assert declared == set(capi.SYMBOLS), declared ^ set(capi.SYMBOLS)
+    for s in declared:
+        assert hasattr(lib, s), s
+    assert b"sm_100a" in lib.atrip_b200_version()
+
+
+def test_create_without_gpu_fails_loudly(lib):
+    import torch
+    if torch.cuda.is_available():
+        return
+    try:
+        capi.Engine(4, 8)
+    except capi.EngineError as e:
+        assert "no CPU fallback" in str(e)
+    else:
+        raise AssertionError("engine creation must fail without a CUDA device")
+
+
+def test_group_and_sort_matches_reference_vectors(lib, golden):
+    for rec in golden["distributions"]:
+        counts = []
+        for me, g in enumerate(rec["nodes"]):
+            tl = capi.host_tuples(capi.GROUP_AND_SORT, rec["Nv"], me, rec["n_nodes"], pad=False)
+            assert len(tl) == g["count"]
+            assert hashlib.sha256(np.ascontiguousarray(tl).tobytes()).hexdigest() == g["sha256"]
+            counts.append(len(tl))
+        # padded lists: same length on every rank, fakes only at the end (Tuples.cxx:346-377)
+        for me in range(rec["n_nodes"]):
+            tl = capi.host_tuples(capi.GROUP_AND_SORT, rec["Nv"], me, rec["n_nodes"], pad=True)
+            assert len(tl) == max(counts)
+            assert np.all(tl[counts[me]:] == 0) and not np.any(np.all(tl[:counts[me]] == 0, axis=1))
+
+
+def test_group_and_sort_partitions_all_tuples(lib, oracle):
+    for Nv, n in [(9, 2), (14, 3), (25, 4), (32, 8), (7, 8)]:
+        parts = [capi.host_tuples(capi.GROUP_AND_SORT, Nv, r, n, pad=False) for r in range(n)]
+        allt = np.concatenate(parts)
+        assert len(allt) == oracle.n_tuples(Nv)
+        assert len({tuple(t) for t in allt.tolist()}) == len(allt)
+        assert np.all(allt[:, 0] <= allt[:, 1]) and np.all(allt[:, 1] <= allt[:, 2])
+        # every tuple has at least one home index on its rank (atrip.org:1938-1942)
+        for r, p in enumerate(parts):
+            assert np.all(np.any(p % n == r, axis=1))
+        # single rank degenerates to the lexicographic list
+    assert np.array_equal(capi.host_tuples(capi.GROUP_AND_SORT, 11, 0, 1), oracle.all_tuples(11))
+
+
+def test_naive_distribution(lib, oracle):
+    Nv, n = 10, 3
+    allt = oracle.all_tuples(Nv)
+    per = -(-len(allt) // n)
+    for r in range(n):
+        tl = capi.host_tuples(capi.NAIVE, Nv, r, n, pad=True)
+        assert len(tl) == per
+        want = allt[per * r: per * (r + 1)]
+        assert np.array_equal(tl[:len(want)], want) and np.all(tl[len(want):] == 0)
+
+
+def test_slice_owner_matches_rankmap(lib, oracle):
+    Nv, n = 37, 8
+    for x in range(0, Nv, 5):
+        assert capi.slice_owner(capi.TA, x, 0, Nv, n) == oracle.L.oracle_owner_single(x, n)
+        for y in range(0, Nv, 7):
+            assert capi.slice_owner(capi.VABCI, x, y, Nv, n) == oracle.L.oracle_owner_pair(x, y, Nv, n)
