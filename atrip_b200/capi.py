@@ -21,7 +21,7 @@ SYMBOLS = [
     "atrip_b200_num_tuples", "atrip_b200_get_tuples", "atrip_b200_run", "atrip_b200_tuple_debug",
     "atrip_b200_read_slice", "atrip_b200_last_timing", "atrip_b200_kp", "atrip_b200_flops_per_tuple",
     "atrip_b200_host_tuples", "atrip_b200_host_slice_owner", "atrip_b200_measure_dmma_peak",
-    "atrip_b200_synth_to_host", "atrip_b200_batch_tuples",
+    "atrip_b200_synth_to_host", "atrip_b200_batch_tuples", "atrip_b200_host_plan",
 ]
 
 NAIVE, GROUP_AND_SORT = 0, 1
@@ -111,6 +111,19 @@ def synth_to_host(device, seed, tensor_id, scale, first, count, host):
     L = load_library()
     if L.atrip_b200_synth_to_host(device, seed, tensor_id, scale, first, count, _ptr(host)) != 0:
         raise EngineError(L.atrip_b200_last_error().decode())
+
+
+def host_plan(No, smem_limit=0):
+    """the contraction kernel's tile plan for No (host-only)"""
+    L = load_library()
+    L.atrip_b200_host_plan.argtypes = [C.c_int64, C.c_int64, C.POINTER(C.c_int64)]
+    out = (C.c_int64 * 11)()
+    if L.atrip_b200_host_plan(No, smem_limit, out) != 0:
+        raise EngineError(L.atrip_b200_last_error().decode())
+    k = ["MI", "NI", "warps", "tu", "tv", "row_tiles", "col_tiles", "stages", "smem", "arows", "useful"]
+    d = dict(zip(k, list(out)))
+    d["useful"] /= 1e6
+    return d
 
 
 def host_tuples(distribution, Nv, rank=0, nranks=1, pad=True):

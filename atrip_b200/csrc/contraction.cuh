@@ -18,7 +18,7 @@
 //
 // Structure (per CTA, persistent over work items = (tuple, class, row tile, column tile)):
 //   warp NW        : producer; one lane issues cp.async.bulk.tensor (TMA, SWIZZLE_128B) for the
-//                    A tile [No*tv rows x 16] and the B tile [<=NI*8 rows x 16] of each K chunk
+//                    A tile [tu*tv rows x 16] and the B tile [<=NI*8 rows x 16] of each K chunk
 //                    into an nstages-deep ring guarded by full/empty mbarriers; it runs ahead
 //                    across work items so the pipe never drains between tiles.
 //   warps 0..NW-1  : consumers; each owns MI x NI DMMA.8x8x4 accumulator fragments
@@ -35,10 +35,11 @@ constexpr int MAX_STAGES = 12;
 struct ContractParams {
   int No, Nv, Kp;
   int nk;       // Kp / KC: K chunks per operand pair (a class runs 2*nk chunks)
-  int tv;       // tile = all u (No) x tv values of v  ->  No*tv rows
-  int mtiles;   // ceil(No / tv)
+  int tu, tv;   // row tile = tu values of u (fast) x tv values of v  ->  tu*tv rows (u + v No = row of C)
+  int utiles;   // ceil(No / tu)
+  int mtiles;   // utiles * ceil(No / tv)
   int ntiles;   // ceil(No / (NI*8))
-  int arows;    // shared-memory rows reserved for A per stage = NW*MI*8 >= No*tv
+  int arows;    // shared-memory rows reserved for A per stage = NW*MI*8 >= tu*tv
   int brows;    // rows of the B TMA box (min(NI*8, No))
   int nstages;
   int ntuples;
@@ -93,7 +94,7 @@ contract_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (warp == nwarps) {
     // ------------------------------------------------------------------ producer
     if (lane == 0) {
-      const uint32_t tx = (uint32_t)((P.No * P.tv + P.brows) * 128);
+      const uint32_t tx = (uint32_t)((P.tu * P.tv + P.brows) * 128);
       const int NvNv = P.Nv * P.Nv;
       for (long long item = blockIdx.x; item < nitems; item += gridDim.x) {
         const int tup = (int)(item / per_tuple);
@@ -116,11 +117,12 @@ contract_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                                                                 : ys[piece] + zs[piece] * P.Nv;
           const int bslot = P.btab[bidx];
           const CUtensorMap *tm = piece ? &tmAT : &tmA;
+          const int u0 = (mt % P.utiles) * P.tu, v0 = (mt / P.utiles) * P.tv;
           for (int kc = 0; kc < P.nk; kc++) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             unsigned char *sb = base + (size_t)stage * stage_bytes;
             mbar_expect_tx(&full_bar[stage], tx);
-            tma_load_4d(sb, tm, &full_bar[stage], kc * KC, 0, mt * P.tv, xslot);
+            tma_load_4d(sb, tm, &full_bar[stage], kc * KC, u0, v0, xslot);
             tma_load_3d(sb + (size_t)P.arows * 128, &tmB, &full_bar[stage], kc * KC, nt * NI * 8, bslot);
             if (++stage == P.nstages) { stage = 0; phase ^= 1; }
           }
@@ -139,7 +141,7 @@ contract_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
   for (int s = 0; s < 4; s++) cs[s] = (uint32_t)(((2 * s + (t >> 1)) ^ perm) * 16);
   const int nchunks = 2 * P.nk;
-  const int tile_rows = P.No * P.tv;
+  const int tile_rows = P.tu * P.tv;
 
   for (long long item = blockIdx.x; item < nitems; item += gridDim.x) {
     const int tup = (int)(item / per_tuple);
@@ -178,13 +180,17 @@ contract_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
     // epilogue: C fragment (row g, cols 2t, 2t+1) -> tile row/col through the same permutation
     double *Rc = P.R + ((size_t)tup * 3 + cls) * cube;
-    const int m0 = mt * tile_rows;
+    const int u0 = (mt % P.utiles) * P.tu, v0 = (mt / P.utiles) * P.tv;
     const int NoNo = P.No * P.No;
+    int ul = (warp * MI * 8 + perm) % P.tu, vl = (warp * MI * 8 + perm) / P.tu;
 #pragma unroll
     for (int i = 0; i < MI; i++) {
       const int rl = warp * MI * 8 + i * 8 + perm;
-      const int m = m0 + rl;
-      if (rl < tile_rows && m < NoNo) {
+      const int u = u0 + ul, v = v0 + vl;
+      const int m = u + v * P.No;
+      ul += 8;
+      while (ul >= P.tu) { ul -= P.tu; vl++; }
+      if (rl < tile_rows && u < P.No && v < P.No) {
 #pragma unroll
         for (int j = 0; j < NI; j++) {
 #pragma unroll

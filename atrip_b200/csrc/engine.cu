@@ -44,51 +44,69 @@ struct KernelVariant {
   const void *fn;
 };
 #define VARIANT(mi, ni, maxt) KernelVariant{mi, ni, maxt, (const void *)contract_kernel<mi, ni, maxt>}
+// accumulators take 4*MI*NI registers; the thread cap follows from the 64K register file
 const KernelVariant kVariants[] = {
-    VARIANT(2, 1, 512), VARIANT(2, 2, 512), VARIANT(2, 3, 512), VARIANT(2, 4, 512), VARIANT(2, 5, 512),
-    VARIANT(2, 6, 512), VARIANT(2, 7, 512), VARIANT(2, 8, 512), VARIANT(2, 10, 416), VARIANT(2, 13, 416),
-    VARIANT(4, 4, 512), VARIANT(4, 5, 384), VARIANT(4, 6, 352), VARIANT(4, 8, 288),
+    VARIANT(2, 1, 512), VARIANT(3, 1, 512), VARIANT(4, 1, 512), VARIANT(5, 1, 512),
+    VARIANT(2, 2, 512), VARIANT(3, 2, 512), VARIANT(4, 2, 512), VARIANT(5, 2, 512),
+    VARIANT(2, 3, 512), VARIANT(3, 3, 512), VARIANT(4, 3, 512), VARIANT(5, 3, 512),
+    VARIANT(2, 4, 512), VARIANT(3, 4, 512), VARIANT(4, 4, 512), VARIANT(5, 4, 416),
+    VARIANT(2, 5, 512), VARIANT(3, 5, 512), VARIANT(4, 5, 416), VARIANT(5, 5, 288),
+    VARIANT(2, 6, 512), VARIANT(3, 6, 416), VARIANT(4, 6, 288), VARIANT(5, 6, 288),
+    VARIANT(2, 7, 512), VARIANT(3, 7, 416), VARIANT(4, 7, 288),
+    VARIANT(2, 8, 512), VARIANT(3, 8, 416), VARIANT(4, 8, 288),
+    VARIANT(2, 10, 416), VARIANT(3, 10, 288),
+    VARIANT(2, 13, 288),
 };
 
 struct ContractPlan {
   const KernelVariant *k = nullptr;
-  int nw = 0, tv = 0, mtiles = 0, ntiles = 0, arows = 0, brows = 0, nstages = 0;
+  int nw = 0, tu = 0, tv = 0, utiles = 0, mtiles = 0, ntiles = 0, arows = 0, brows = 0, nstages = 0;
   size_t smem = 0;
   double useful = 0;
 };
 
+// Pick the kernel variant, consumer-warp count and row tile (tu x tv) for this No.
+//   useful   = fraction of issued DMMA work that lands inside the No^2 x No class matrix
+//   smsp_eff = consumer warps are dealt round-robin to the 4 SM sub-partitions, each with its own
+//              tensor pipe: NW % 4 != 0 leaves pipes idle (ncu r01: NW = 10 -> 81.6 % DMMA active)
+//   warp_eff = tools/fp64_peak.cu: one warp per sub-partition reaches ~89 % of the DMMA ceiling,
+//              two or more reach it
 ContractPlan plan_contraction(int No, size_t smem_limit) {
   ContractPlan best;
   double best_score = -1;
   for (const auto &k : kVariants) {
     const int ntiles = (No + k.NI * 8 - 1) / (k.NI * 8);
-    for (int nw = 2; nw <= k.maxt / 32 - 1; nw++) {
+    for (int nw = 4; nw <= k.maxt / 32 - 1; nw++) {
       const int arows = nw * k.MI * 8;
-      int tv = std::min(No, arows / No);
-      if (tv < 1) continue;
-      tv = std::min(tv, 256);
-      const int mtiles = (No + tv - 1) / tv;
       const size_t stage = contract_stage_bytes(arows, k.NI);
-      int nstages = (int)std::min<size_t>(MAX_STAGES, (smem_limit - 2048) / stage);
+      const int nstages = (int)std::min<size_t>(MAX_STAGES, (smem_limit - 2048) / stage);
       if (nstages < 3) continue;
-      const double useful = (double)No * No * No / ((double)mtiles * arows * ntiles * k.NI * 8);
-      // measured (tools/fp64_peak.cu): 4 consumer warps reach ~89 % of DMMA peak, >= 8 reach it
-      const double warp_eff = nw >= 8 ? 1.0 : (nw >= 6 ? 0.97 : (nw >= 4 ? 0.89 : 0.6));
-      // fewer LDS per DMMA and fewer barrier trips with larger fragments grids
-      const double frag_eff = 1.0 - 0.04 / (k.MI * k.NI) * 8;
-      const double score = useful * warp_eff * frag_eff;
-      if (score > best_score + 1e-9) {
-        best_score = score;
-        best.k = &k;
-        best.nw = nw;
-        best.tv = tv;
-        best.mtiles = mtiles;
-        best.ntiles = ntiles;
-        best.arows = arows;
-        best.brows = std::min(k.NI * 8, No);
-        best.nstages = nstages;
-        best.smem = stage * nstages + 1024;
-        best.useful = useful;
+      const double smsp_eff = (double)nw / (4.0 * ((nw + 3) / 4));
+      const double warp_eff = nw >= 8 ? 1.0 : 0.89;
+      const double stage_eff = nstages >= 4 ? 1.0 : 0.97;
+      // fewer LDS per DMMA with larger fragment grids (smem bandwidth headroom)
+      const double frag_eff = 1.0 - 0.02 * (k.MI + k.NI) / (double)(k.MI * k.NI);
+      for (int tu = std::min(std::min(No, 256), arows); tu >= 1; tu--) {  // ties: prefer long u runs
+        const int tv = std::min(std::min(No, 256), arows / tu);
+        const int utiles = (No + tu - 1) / tu, vtiles = (No + tv - 1) / tv;
+        const double useful =
+            (double)No * No * No / ((double)utiles * vtiles * arows * ntiles * k.NI * 8);
+        const double score = useful * smsp_eff * warp_eff * stage_eff * frag_eff;
+        if (score > best_score + 1e-9) {
+          best_score = score;
+          best.k = &k;
+          best.nw = nw;
+          best.tu = tu;
+          best.tv = tv;
+          best.utiles = utiles;
+          best.mtiles = utiles * vtiles;
+          best.ntiles = ntiles;
+          best.arows = arows;
+          best.brows = std::min(k.NI * 8, No);
+          best.nstages = nstages;
+          best.smem = stage * nstages + 1024;
+          best.useful = useful;
+        }
       }
     }
   }
@@ -185,7 +203,7 @@ void build_maps(atrip_b200_ctx *c, double *AX, double *BY, CUtensorMap *tA, CUte
     const uint64_t dims[4] = {Kp, No, No, c->nX};
     const uint64_t strP[3] = {Kp * 8, No * Kp * 8, No * No * Kp * 8};
     const uint64_t strT[3] = {No * Kp * 8, Kp * 8, No * No * Kp * 8};
-    const uint32_t box[4] = {KC, (uint32_t)No, (uint32_t)c->plan.tv, 1};
+    const uint32_t box[4] = {KC, (uint32_t)c->plan.tu, (uint32_t)c->plan.tv, 1};
     make_map(tA, AX, 4, dims, strP, box);
     make_map(tAT, AX, 4, dims, strT, box);
   }
@@ -246,7 +264,9 @@ void launch_contract(atrip_b200_ctx *c, const int4 *d_tuples, int ntuples, bool 
   P.Nv = c->Nv;
   P.Kp = c->Kp;
   P.nk = c->Kp / KC;
+  P.tu = c->plan.tu;
   P.tv = c->plan.tv;
+  P.utiles = c->plan.utiles;
   P.mtiles = c->plan.mtiles;
   P.ntiles = c->plan.ntiles;
   P.arows = c->plan.arows;
@@ -279,6 +299,9 @@ ReduceParams reduce_params(atrip_b200_ctx *c, const int4 *d_tuples, int ntuples,
   P.VIJ = c->VIJ;
   P.vtab = c->vtab;
   P.e_tuple = c->e_tuple;
+  // enough CTAs to fill the GPU a few times over even when a batch has few tuples (large No)
+  const int nb = (c->No + RT - 1) / RT, orbits = nb * (nb + 1) * (nb + 2) / 6;
+  P.nsplit = std::max(1, std::min(std::min(orbits, 64), (c->nsm * 6 + ntuples - 1) / std::max(1, ntuples)));
   return P;
 }
 
@@ -286,10 +309,11 @@ void launch_reduce(atrip_b200_ctx *c, const int4 *d_tuples, int ntuples, bool ct
   if (ntuples <= 0) return;
   ReduceParams P = reduce_params(c, d_tuples, ntuples, ct);
   const size_t smem = reduce_smem_bytes(c->No, ct);
-  if (ct) reduce_kernel<true><<<ntuples, REDUCE_THREADS, smem, c->stream>>>(P);
-  else reduce_kernel<false><<<ntuples, REDUCE_THREADS, smem, c->stream>>>(P);
+  const dim3 grid(ntuples, P.nsplit);
+  if (ct) reduce_kernel<true><<<grid, REDUCE_THREADS, smem, c->stream>>>(P);
+  else reduce_kernel<false><<<grid, REDUCE_THREADS, smem, c->stream>>>(P);
   CUDA_OK(cudaGetLastError());
-  accumulate_kernel<<<1, 256, 0, c->stream>>>(c->e_tuple, ntuples, total);
+  accumulate_kernel<<<1, 256, 0, c->stream>>>(c->e_tuple, ntuples * P.nsplit, total);
   CUDA_OK(cudaGetLastError());
 }
 
@@ -412,7 +436,7 @@ void create_impl(atrip_b200_ctx *c) {
   c->batch = (int)std::max<long long>(1, batch);
   c->R = dalloc<double>(cube3 * c->batch);
   if (cfg.with_J) c->RJ = dalloc<double>(cube3 * c->batch);
-  c->e_tuple = dalloc<double>(c->batch);
+  c->e_tuple = dalloc<double>((size_t)c->batch * 64);
   c->d_total = dalloc<double>(2);
   c->dbg_tuple = dalloc<int4>(1);
 
@@ -846,6 +870,22 @@ int atrip_b200_synth_to_host(int32_t device, uint64_t seed, int32_t tensor_id, d
     }
     cudaFree(d);
   });
+}
+
+int atrip_b200_host_plan(int64_t No, int64_t smem_limit_bytes, int64_t *out) {
+  if (No < 1 || No > 256) {
+    g_error = "atrip_b200_host_plan: No must be in [1, 256]";
+    return 1;
+  }
+  const ContractPlan p = plan_contraction((int)No, smem_limit_bytes > 0 ? (size_t)smem_limit_bytes : 232448);
+  if (!p.k) {
+    g_error = "no contraction kernel variant fits";
+    return 1;
+  }
+  const int64_t v[11] = {p.k->MI, p.k->NI, p.nw, p.tu, p.tv, p.mtiles, p.ntiles, p.nstages, (int64_t)p.smem,
+                         p.arows, (int64_t)(p.useful * 1e6)};
+  for (int i = 0; i < 11; i++) out[i] = v[i];
+  return 0;
 }
 
 int64_t atrip_b200_host_tuples(int32_t distribution, int64_t Nv, int32_t rank, int32_t nranks, int32_t pad,

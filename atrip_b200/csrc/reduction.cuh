@@ -31,7 +31,8 @@ struct ReduceParams {
   const double *eps_i, *eps_a, *Tai;
   const double *VIJ;  // Vabij pair blocks [slot][No^2]
   const int *vtab;    // y + z Nv -> slot
-  double *e_tuple;    // [ntuples]
+  double *e_tuple;    // [ntuples * nsplit] partial energies
+  int nsplit;         // CTAs per tuple: CTA (t, s) takes the orbits o with o % nsplit == s
 };
 
 __host__ __device__ inline size_t reduce_smem_bytes(int No, bool ct) {
@@ -40,7 +41,7 @@ __host__ __device__ inline size_t reduce_smem_bytes(int No, bool ct) {
 
 
 template <bool CT>
-__global__ void __launch_bounds__(REDUCE_THREADS)
+__global__ void __launch_bounds__(REDUCE_THREADS, 3)
 reduce_kernel(const ReduceParams P) {
   extern __shared__ double sm[];
   double *Wt = sm;                               // [6][RTILE]
@@ -53,8 +54,9 @@ reduce_kernel(const ReduceParams P) {
   const int tup = blockIdx.x;
   const int4 abc = P.tuples[tup];
   const int tid = threadIdx.x;
+  const int split = blockIdx.y;
   if (abc.x == 0 && abc.y == 0 && abc.z == 0) {  // FAKE_TUPLE contributes nothing (Atrip.cxx:629)
-    if (tid == 0) P.e_tuple[tup] = 0.0;
+    if (tid == 0) P.e_tuple[(size_t)tup * P.nsplit + split] = 0.0;
     return;
   }
   const int a = abc.x, b = abc.y, c = abc.z;
@@ -78,11 +80,20 @@ reduce_kernel(const ReduceParams P) {
   double esum = 0.0;
   const int l0 = tid & 7, l1 = (tid >> 3) & 7, l2 = tid >> 6;  // l2 in 0..3
 
+  __syncthreads();  // publishes sEps, sTa, sTb, sTc
+  int orbit = -1;
   for (int I = 0; I < nb; I++)
     for (int J = 0; J <= I; J++)
       for (int K = 0; K <= J; K++) {
+        if (++orbit % P.nsplit != split) continue;
         const int blk[3] = {I, J, K};
-        __syncthreads();  // previous orbit fully consumed (also publishes sEps.. on first trip)
+        // coincident block coordinates give identical tiles: build each distinct one once
+        // (tile p of 0 (I,J,K) 1 (I,K,J) 2 (J,I,K) 3 (J,K,I) 4 (K,I,J) 5 (K,J,I) -> canon[p])
+        const bool eIJ = (I == J), eJK = (J == K);
+        const int c1 = eJK ? 0 : 1, c2 = eIJ ? 0 : 2, c3 = (eIJ && eJK) ? 0 : (eIJ ? 1 : 3),
+                  c4 = (eIJ && eJK) ? 0 : (eJK ? 2 : 4), c5 = (eIJ && eJK) ? 0 : (eIJ ? 4 : (eJK ? 3 : 5));
+        const int canon[6] = {0, c1, c2, c3, c4, c5};
+        __syncthreads();  // previous orbit fully consumed
         // ---- pass 1: tiles <- C_k[x,y,z] + C_j[x,z,y]   (lanes run along x)
 #pragma unroll
         for (int X = 0; X < 3; X++)
@@ -91,6 +102,7 @@ reduce_kernel(const ReduceParams P) {
             if (Y == X) continue;
             const int Z = 3 - X - Y;
             const int pi = X * 2 + ((Y > Z) ? 1 : 0);
+            if (canon[pi] != pi) continue;
             const int x = blk[X] * RT + l0, y = blk[Y] * RT + l1;
 #pragma unroll
             for (int it = 0; it < 2; it++) {
@@ -121,6 +133,7 @@ reduce_kernel(const ReduceParams P) {
             if (Y == X) continue;
             const int Z = 3 - X - Y;
             const int pi = X * 2 + ((Y > Z) ? 1 : 0);
+            if (canon[pi] != pi) continue;
             const int y = blk[Y] * RT + l0, z = blk[Z] * RT + l1;
 #pragma unroll
             for (int it = 0; it < 2; it++) {
@@ -141,10 +154,10 @@ reduce_kernel(const ReduceParams P) {
           const int i = I * RT + il, j = J * RT + jl, k = K * RT + kl;
           if (i < No && j <= i && k <= j) {
             // tiles: 0 (I,J,K) 1 (I,K,J) 2 (J,I,K) 3 (J,K,I) 4 (K,I,J) 5 (K,J,I)
-            const int o0 = il + RS1 * jl + RS2 * kl, o1 = il + RS1 * kl + RS2 * jl;
-            const int o2 = RTILE * 2 + jl + RS1 * il + RS2 * kl, o3 = RTILE * 3 + jl + RS1 * kl + RS2 * il;
-            const int o4 = RTILE * 4 + kl + RS1 * il + RS2 * jl, o5 = RTILE * 5 + kl + RS1 * jl + RS2 * il;
-            const double A = Wt[o0], B = Wt[RTILE + o1], C = Wt[o2], D = Wt[o3], E = Wt[o4], F = Wt[o5];
+            const int o0 = il + RS1 * jl + RS2 * kl, o1 = RTILE * c1 + il + RS1 * kl + RS2 * jl;
+            const int o2 = RTILE * c2 + jl + RS1 * il + RS2 * kl, o3 = RTILE * c3 + jl + RS1 * kl + RS2 * il;
+            const int o4 = RTILE * c4 + kl + RS1 * il + RS2 * jl, o5 = RTILE * c5 + kl + RS1 * jl + RS2 * il;
+            const double A = Wt[o0], B = Wt[o1], C = Wt[o2], D = Wt[o3], E = Wt[o4], F = Wt[o5];
             // Vabij entries; pair blocks: 0 (I,J) 1 (I,K) 2 (J,I) 3 (J,K) 4 (K,I) 5 (K,J)
             const int pij = 0 * 64 + il + 8 * jl, pik = 1 * 64 + il + 8 * kl, pji = 2 * 64 + jl + 8 * il;
             const int pjk = 3 * 64 + jl + 8 * kl, pki = 4 * 64 + kl + 8 * il, pkj = 5 * 64 + kl + 8 * jl;
@@ -154,7 +167,7 @@ reduce_kernel(const ReduceParams P) {
             const double tci = sTc[i], tcj = sTc[j], tck = sTc[k];
             // Z[x,y,z] = T[x,y,z] + Tai[a,x] Vbc[y,z] + Tai[b,y] Vac[x,z] + Tai[c,z] Vab[x,y]
             // (Equations.cxx:420-422, three separate += in this order)
-            double U = Zt[o0], V = Zt[RTILE + o1], W = Zt[o2], X = Zt[o3], Y = Zt[o4], Z = Zt[o5];
+            double U = Zt[o0], V = Zt[o1], W = Zt[o2], X = Zt[o3], Y = Zt[o4], Z = Zt[o5];
             U = ((U + tai * Vbc[pjk]) + tbj * Vac[pik]) + tck * Vab[pij];  // Z[i,j,k]
             V = ((V + tai * Vbc[pkj]) + tbk * Vac[pij]) + tcj * Vab[pik];  // Z[i,k,j]
             W = ((W + taj * Vbc[pik]) + tbi * Vac[pjk]) + tck * Vab[pji];  // Z[j,i,k]
@@ -189,7 +202,7 @@ reduce_kernel(const ReduceParams P) {
   if (tid == 0) {
     double s = 0.0;
     for (int w = 0; w < REDUCE_THREADS / 32; w++) s += sRed[w];
-    P.e_tuple[tup] = s;
+    P.e_tuple[(size_t)tup * P.nsplit + split] = s;
   }
 }
 

@@ -117,6 +117,11 @@ int atrip_b200_measure_dmma_peak(int32_t device, double *tflops);
 int atrip_b200_synth_to_host(int32_t device, uint64_t seed, int32_t tensor_id, double scale, uint64_t first,
                              uint64_t count, double *host);
 
+/*      contraction-kernel plan chosen for No (host-only, DESIGN.md "Tile planner"):
+ *      out[0..10] = MI, NI, consumer warps, tu, tv, row tiles, column tiles, pipeline stages,
+ *      dynamic shared memory bytes, A rows per stage, useful-DMMA fraction x 1e6 */
+int atrip_b200_host_plan(int64_t No, int64_t smem_limit_bytes, int64_t *out11);
+
 /* ---- host-only utilities (no device needed; usable before any context exists)
  *      tuple list of rank `rank` of `nranks` (3 x uint64 per tuple, padded with the fake tuple
  *      when pad != 0); returns the list length, writes at most cap tuples.
