@@ -21,7 +21,7 @@ SYMBOLS = [
     "atrip_b200_num_tuples", "atrip_b200_get_tuples", "atrip_b200_run", "atrip_b200_tuple_debug",
     "atrip_b200_read_slice", "atrip_b200_last_timing", "atrip_b200_kp", "atrip_b200_flops_per_tuple",
     "atrip_b200_host_tuples", "atrip_b200_host_slice_owner", "atrip_b200_measure_dmma_peak",
-    "atrip_b200_synth_to_host", "atrip_b200_batch_tuples", "atrip_b200_host_plan",
+    "atrip_b200_synth_to_host", "atrip_b200_batch_tuples", "atrip_b200_host_plan", "atrip_b200_device_count",
 ]
 
 NAIVE, GROUP_AND_SORT = 0, 1

@@ -720,6 +720,14 @@ extern "C" {
 
 const char *atrip_b200_last_error(void) { return g_error.c_str(); }
 const char *atrip_b200_version(void) { return "atrip_b200 0.1 (sm_100a)"; }
+int32_t atrip_b200_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
 
 int atrip_b200_create(atrip_b200_ctx **out, const atrip_b200_config *cfg) {
   if (!out || !cfg) {

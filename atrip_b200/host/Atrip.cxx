@@ -1,0 +1,243 @@
+// Host side of the B200 build of atrip: atrip::Atrip::init / run<F> over the C-ABI device engine
+// (include/atrip_b200.h).  Mirrors what the reference's orchestrator does at its boundary
+// (src/atrip/Atrip.cxx:54-63, 65-1133) -- sizes from the epsilon tensors, replicated small
+// tensors, slicing of the four big tensors, tuple distribution, checkpoint, progress callback,
+// max_iterations, energy reduction and sign -- while the per-tuple work, the slice stores and
+// the tuple schedule live on the device.
+#include <chrono>
+#include <cstdlib>
+#include <fstream>
+#include <iomanip>
+#include <memory>
+#include <vector>
+
+#include <atrip/Atrip.hpp>
+#include <atrip/Checkpoint.hpp>
+#include <atrip_b200.h>
+
+namespace atrip {
+
+size_t Atrip::rank = 0;
+size_t Atrip::np = 1;
+MPI_Comm Atrip::communicator;
+std::map<std::string, double> Atrip::chrono;
+IterationDescriptor IterationDescription::descriptor;
+
+void register_iteration_descriptor(IterationDescriptor d) { IterationDescription::descriptor = d; }
+
+// reference Atrip.cxx:54-63
+void Atrip::init(MPI_Comm world) {
+  Atrip::communicator = world;
+  int r = 0, n = 1;
+  MPI_Comm_rank(world, &r);
+  MPI_Comm_size(world, &n);
+  Atrip::rank = (size_t)r;
+  Atrip::np = (size_t)n;
+}
+
+namespace {
+
+struct Seconds {
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  double operator()() const { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); }
+};
+
+void ok(int rc, const char *what) {
+  if (rc != 0) throw std::string("atrip_b200: ") + what + ": " + atrip_b200_last_error();
+}
+
+// full column-major contents of a CTF tensor on this rank.  The dense single-process shim
+// exposes its storage; a real (distributed) CTF tensor is gathered with read_all, which is what
+// the reference does for the replicated tensors (Atrip.cxx:179-181).
+struct HostView {
+  const double *ptr = nullptr;
+  std::vector<double> owned;
+};
+HostView view(CTF::Tensor<double> *t) {
+  HostView v;
+  if (!t) return v;
+#ifdef ATRIP_B200_DENSE_CTF_HPP
+  v.ptr = t->data;
+#else
+  int64_t n = 1;
+  for (int i = 0; i < t->order; i++) n *= t->lens[i];
+  v.owned.resize((size_t)n);
+  t->read_all(v.owned.data());
+  v.ptr = v.owned.data();
+#endif
+  return v;
+}
+
+struct EngineHandle {
+  atrip_b200_ctx *ctx = nullptr;
+  ~EngineHandle() {
+    if (ctx) atrip_b200_destroy(ctx);
+  }
+};
+
+}  // namespace
+
+template <>
+Atrip::Output Atrip::run<double>(Atrip::Input<double> const &in) {
+  if (!in.ei || !in.ea || !in.Tph || !in.Tpphh || !in.Vpphh || !in.Vhhhp || !in.Vppph)
+    throw std::string("atrip: epsilon_i, epsilon_a, Tai, Tabij, Vabij, Vijka and Vabci are all required");
+  const size_t No = (size_t)in.ei->lens[0], Nv = (size_t)in.ea->lens[0];  // Atrip.cxx:72-73
+  LOG(0, "Atrip") << "No: " << No << "\n";
+  LOG(0, "Atrip") << "Nv: " << Nv << "\n";
+  LOG(0, "Atrip") << "np: " << Atrip::np << "\n";
+  Atrip::chrono.clear();
+  Seconds total;
+
+  // one rank per GPU, device = rank % cards (Atrip.cxx:84-91, 119)
+  const int ncards = atrip_b200_device_count();
+  if (ncards == 0)
+    throw std::string("atrip: no CUDA device visible to this rank; the B200 build has no CPU path");
+  const bool with_J = in.Jppph && in.Jhhhp;  // both needed for the (cT) pass (Atrip.cxx:338-362)
+  atrip_b200_config cfg{};
+  cfg.device = (int32_t)(Atrip::rank % (size_t)ncards);
+  cfg.rank = (int32_t)Atrip::rank;
+  cfg.nranks = (int32_t)Atrip::np;
+  cfg.with_J = with_J;
+  cfg.No = (int64_t)No;
+  cfg.Nv = (int64_t)Nv;
+  cfg.batch_tuples = 0;
+  cfg.resident = 1;
+  EngineHandle eng;
+  ok(atrip_b200_create(&eng.ctx, &cfg), "create");
+  LOG(0, "Atrip") << "engine: " << atrip_b200_version() << " on device " << cfg.device << "\n";
+
+  {  // replicated tensors (Atrip.cxx:176-215); Tai is negated for the ijkabc algorithm (:183-187)
+    Seconds t;
+    HostView ei = view(in.ei), ea = view(in.ea), tph = view(in.Tph);
+    ok(atrip_b200_set_epsilon(eng.ctx, ei.ptr, ea.ptr), "set_epsilon");
+    if (in.ijkabc) {
+      std::vector<double> neg(tph.ptr, tph.ptr + No * Nv);
+      for (auto &x : neg) x = -x;
+      ok(atrip_b200_set_Tai(eng.ctx, neg.data()), "set_Tai");
+    } else {
+      ok(atrip_b200_set_Tai(eng.ctx, tph.ptr), "set_Tai");
+    }
+    // the four big tensors -> HBM stores (replaces the five SliceUnion ctors, Atrip.cxx:277-332)
+    {
+      HostView v = view(in.Vppph);
+      ok(atrip_b200_load_Vabci(eng.ctx, v.ptr), "load_Vabci");
+    }
+    if (in.delete_Vppph) delete in.Vppph;  // Atrip.cxx:310
+    {
+      HostView v = view(in.Tpphh);
+      ok(atrip_b200_load_Tabij(eng.ctx, v.ptr), "load_Tabij");
+    }
+    {
+      HostView v = view(in.Vpphh);
+      ok(atrip_b200_load_Vabij(eng.ctx, v.ptr), "load_Vabij");
+    }
+    {
+      HostView v = view(in.Vhhhp);
+      ok(atrip_b200_load_Vijka(eng.ctx, v.ptr), "load_Vijka");
+    }
+    if (with_J) {
+      HostView j1 = view(in.Jhhhp), j2 = view(in.Jppph);
+      ok(atrip_b200_load_Jijka(eng.ctx, j1.ptr), "load_Jijka");
+      ok(atrip_b200_load_Jabci(eng.ctx, j2.ptr), "load_Jabci");
+    }
+    Atrip::chrono["slicing"] = t();
+  }
+
+  {  // tuple distribution (Atrip.cxx:383-399)
+    Seconds t;
+    ok(atrip_b200_build_tuples(eng.ctx, in.tuples_distribution == Input<double>::GROUP_AND_SORT ? 1 : 0),
+       "build_tuples");
+    Atrip::chrono["tuples:build"] = t();
+  }
+  const size_t n_iterations = (size_t)atrip_b200_num_tuples(eng.ctx);
+  LOG(0, "Atrip") << "#iterations: " << n_iterations << "\n";
+  const double doubles_flops = atrip_b200_flops_per_tuple(eng.ctx) / 1e9;  // GF per tuple, Atrip.cxx:578-580
+
+  // checkpoint (Atrip.cxx:586-621): resume at the stored iteration, rank 0 seeds its energy
+  Output local{0, 0};
+  size_t first_iteration = 0;
+  const size_t checkpoint_mod = in.checkpoint_at_every_iteration != 0
+                                    ? in.checkpoint_at_every_iteration
+                                    : (size_t)(n_iterations * in.checkpoint_at_percentage / 100);
+  if (in.read_checkpoint_if_exists) {
+    std::ifstream fin(in.checkpoint_path);
+    if (fin.is_open()) {
+      LOG(0, "Atrip") << "Reading checkpoint from " << in.checkpoint_path << "\n";
+      const Checkpoint c = read_checkpoint(fin);
+      if (c.no != No || c.nv != Nv || c.iteration > n_iterations)
+        throw std::string("atrip: checkpoint ") + in.checkpoint_path + " does not belong to this calculation";
+      first_iteration = c.iteration;
+      if (Atrip::rank == 0) local.energy = -c.energy;  // stored energy is the physical one
+      LOG(0, "Atrip") << "iteration from checkpoint " << first_iteration << "\n";
+    }
+  }
+
+  // iteration range: the reference leaves its loop after iteration index max_iterations
+  // (Atrip.cxx:1052-1056), i.e. max_iterations + 1 tuples are processed
+  size_t last = n_iterations;
+  if (in.max_iterations != 0) last = std::min(n_iterations, in.max_iterations + 1);
+
+  // reports every iteration_mod iterations or percentage_mod percent (Atrip.cxx:402-405, 734)
+  size_t report_mod = 0;
+  if (in.percentage_mod > 0) report_mod = std::max<size_t>(1, n_iterations * (size_t)in.percentage_mod / 100);
+  else if (in.iteration_mod > 0) report_mod = (size_t)in.iteration_mod;
+  size_t chunk = last > first_iteration ? last - first_iteration : 0;
+  if (report_mod) chunk = std::min(chunk, report_mod);
+  if (checkpoint_mod && in.writeCheckpoint) chunk = std::min(chunk, checkpoint_mod);
+
+  Seconds loop;
+  double device_ms = 0, tuples_done = 0;
+  for (size_t it = first_iteration; it < last;) {
+    const size_t n = std::min(chunk, last - it);
+    double e = 0, ect = 0;
+    ok(atrip_b200_run(eng.ctx, (int64_t)it, (int64_t)n, &e, &ect), "run");
+    double tm[6];
+    atrip_b200_last_timing(eng.ctx, tm);
+    device_ms += tm[0];
+    tuples_done += tm[5];
+    local.energy += e;
+    local.ct_energy += ect;
+    it += n;
+    if (in.barrier) MPI_Barrier(Atrip::communicator);
+    if (report_mod && (it % report_mod == 0 || it == last)) {
+      if (IterationDescription::descriptor) IterationDescription::descriptor({it, n_iterations, loop()});
+      LOG(0, "Atrip") << "iteration " << it << " [" << 100 * it / std::max<size_t>(1, n_iterations) << "%] ("
+                      << (device_ms > 0 ? doubles_flops * tuples_done / (device_ms * 1e-3) : -1) << "GF)\n";
+    }
+    if (checkpoint_mod && in.writeCheckpoint && it < last && it % checkpoint_mod == 0) {
+      double global = 0;
+      MPI_Reduce(&local.energy, &global, 1, MPI_DOUBLE, MPI_SUM, 0, Atrip::communicator);
+      if (Atrip::rank == 0)
+        write_checkpoint({No, Nv, 1, Atrip::np, -global, it, in.rank_round_robin}, in.checkpoint_path);
+    }
+  }
+  Atrip::chrono["iterations"] = loop();
+  Atrip::chrono["device"] = device_ms * 1e-3;
+
+  // energy reduction and sign (Atrip.cxx:1094-1111)
+  Output global{0, 0};
+  MPI_Reduce(&local.energy, &global.energy, 1, MPI_DOUBLE, MPI_SUM, 0, Atrip::communicator);
+  MPI_Reduce(&local.ct_energy, &global.ct_energy, 1, MPI_DOUBLE, MPI_SUM, 0, Atrip::communicator);
+  if (!in.ijkabc) {
+    global.energy = -global.energy;
+    global.ct_energy = -global.ct_energy;
+  }
+  Atrip::chrono["total"] = total();
+
+  // the reference leaves std::cout at 15 digits for its caller's "Energy:" line
+  LOG(0, "Atrip") << "Energy: " << std::setprecision(15) << std::setw(23) << global.energy << std::endl;
+  if (in.chrono)
+    for (auto const &p : Atrip::chrono) LOG(1, " ") << p.first << " :: " << p.second << std::endl;
+  LOG(0, "atrip:flops(doubles)") << (device_ms > 0 ? tuples_done * doubles_flops / (device_ms * 1e-3) : 0) << "\n";
+  LOG(0, "atrip:flops(iterations)") << tuples_done * doubles_flops / std::max(1e-9, Atrip::chrono["iterations"]) << "\n";
+  return global;
+}
+
+// The complex instantiation exists so that drivers templated on the field link
+// (reference Atrip.cxx:1135-1136); the B200 engine implements the FP64 real case.
+template <>
+Atrip::Output Atrip::run<Complex>(Atrip::Input<Complex> const &) {
+  throw std::string("atrip (B200 build): run<Complex> is not implemented; only FP64 real (SURVEY.md 8f rank 4)");
+}
+
+}  // namespace atrip

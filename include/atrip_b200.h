@@ -42,6 +42,8 @@ int atrip_b200_create(atrip_b200_ctx **ctx, const atrip_b200_config *cfg);
 int atrip_b200_destroy(atrip_b200_ctx *ctx);
 const char *atrip_b200_last_error(void);
 const char *atrip_b200_version(void);
+/* number of usable CUDA devices (0 if none; replaces cuDeviceGetCount, Atrip.cxx:82) */
+int32_t atrip_b200_device_count(void);
 
 /* ---- replicated small tensors (replaces read_all + HtoD, Atrip.cxx:176-215); host pointers */
 int atrip_b200_set_epsilon(atrip_b200_ctx *ctx, const double *eps_i, const double *eps_a);

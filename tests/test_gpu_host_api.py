@@ -1,0 +1,76 @@
+"""GPU: the C++ drop-in boundary.  atrip::Atrip::run<double> (include/atrip/Atrip.hpp,
+atrip_b200/host/Atrip.cxx) through the same calls the reference's bench makes, and the
+reference's own bench/main.cxx compiled unchanged against that API (built where
+/root/reference exists; the binary travels to the GPU box)."""
+import os
+import re
+import subprocess
+
+import pytest
+
+from conftest import ROOT, fh
+
+pytestmark = pytest.mark.gpu
+HOST = os.path.join(ROOT, "atrip_b200", "host")
+
+
+def run(cmd, **kw):
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, **kw)
+    return p.returncode, p.stdout + p.stderr
+
+
+def result(out):
+    m = re.search(r"RESULT energy (\S+) \S+ ct_energy (\S+)", out)
+    assert m, out
+    return fh(m.group(1)), fh(m.group(2))
+
+
+@pytest.fixture(scope="module")
+def driver():
+    exe = os.path.join(HOST, "synth_driver")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-s", "-C", HOST, "libatrip.so", "synth_driver"])
+    return exe
+
+
+def test_atrip_run_matches_reference_vectors(driver, golden):
+    """Atrip::Input -> Atrip::run -> Output on host CTF tensors; energies of the reference"""
+    for r in golden["runs"]:
+        cmd = [driver, str(r["No"]), str(r["Nv"]), str(r["seed"]), repr(r["scale"]), "0", "group"]
+        if r["with_J"]:
+            cmd.append("cT")
+        rc, out = run(cmd)
+        assert rc == 0, out
+        e, ct = result(out)
+        ref, ref_ct = fh(r["energy"]), fh(r["ct_energy"])
+        assert abs(e - ref) <= 1e-10 and abs(e - ref) <= 1e-12 * abs(ref), (r, e)
+        assert abs(ct - ref_ct) <= 1e-10 and abs(ct - ref_ct) <= 1e-11 * max(abs(ref), abs(ref_ct)), (r, ct)
+        assert "Atrip: Energy:" in out and "atrip:flops(doubles)" in out
+
+
+def test_atrip_run_naive_equals_group(driver):
+    """both distributions enumerate the same tuples at np=1 (Tuples.cxx:89-141, 310-407)"""
+    e1 = result(run([driver, "6", "15", "3", "0.05", "0", "group"])[1])
+    e2 = result(run([driver, "6", "15", "3", "0.05", "0", "naive"])[1])
+    assert abs(e1[0] - e2[0]) <= 1e-13 * abs(e1[0])
+
+
+def test_max_iterations_follows_reference(driver, oracle):
+    """the reference leaves its loop after iteration index max_iterations, i.e. processes
+    max_iterations + 1 tuples (Atrip.cxx:1052-1056)"""
+    No, Nv, seed, scale, mx = 6, 15, 3, 0.05, 40
+    e, _ = result(run([driver, str(No), str(Nv), str(seed), repr(scale), str(mx), "group"])[1])
+    t = oracle.inputs(No, Nv, seed=seed, scale=scale)
+    want, _ = oracle.run(No, Nv, t, tuples=oracle.all_tuples(Nv)[:mx + 1])
+    assert abs(e - want) <= 1e-12 * abs(want)
+
+
+def test_reference_bench_driver_runs_against_this_api():
+    exe = os.path.join(HOST, "atrip_bench")
+    if not os.path.exists(exe):
+        pytest.skip("atrip_bench is built only where /root/reference is present")
+    rc, out = run([exe, "--no", "6", "--nv", "20", "--dist", "group", "--nocheckpoint", "-%", "50"], cwd="/tmp")
+    assert rc == 0, out
+    assert "Atrip throwed" not in out, out
+    assert re.search(r"^Energy: ", out, re.M) and re.search(r"^Energy \(cT\): ", out, re.M), out
+    assert "Progress(%)" in out  # the driver's register_iteration_descriptor callback fired
