@@ -35,7 +35,7 @@ sys.path.insert(0, ROOT)
 
 CONFIGS = {  # BASELINE.json configs; scale keeps |E| = O(1e-2..1) for the parity checks
     "c1": dict(No=10, Nv=40, scale=0.01, tuples_per_step=11440, desc="No=10 Nv=40 (CPU-runnable case)"),
-    "c2": dict(No=40, Nv=400, scale=0.001, tuples_per_step=98304, desc="No=40 Nv=400 FP64 random tensors"),
+    "c2": dict(No=40, Nv=400, scale=0.001, tuples_per_step=196608, desc="No=40 Nv=400 FP64 random tensors"),
     "c5s": dict(No=32, Nv=480, scale=0.001, tuples_per_step=98304, desc="No=32 high Nv/No (c5 scaled to 1 GPU)"),
 }
 SEED = 12345
