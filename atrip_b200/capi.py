@@ -22,10 +22,14 @@ SYMBOLS = [
     "atrip_b200_read_slice", "atrip_b200_last_timing", "atrip_b200_kp", "atrip_b200_flops_per_tuple",
     "atrip_b200_host_tuples", "atrip_b200_host_slice_owner", "atrip_b200_measure_dmma_peak",
     "atrip_b200_synth_to_host", "atrip_b200_batch_tuples", "atrip_b200_host_plan", "atrip_b200_device_count",
+    "atrip_b200_comm_unique_id", "atrip_b200_comm_init", "atrip_b200_allreduce", "atrip_b200_last_exchange",
+    "atrip_b200_host_slice_slot", "atrip_b200_host_shard_sizes", "atrip_b200_host_plan_batch",
+    "atrip_b200_host_cache_need", "atrip_b200_host_local_slot",
 ]
 
 NAIVE, GROUP_AND_SORT = 0, 1
 TA, VIJKA, VABCI, TABIJ, VABIJ = 100, 101, 200, 201, 202
+VABCI_T = 203  # host-side name of the transposed-hole twin (x,x)' of a diagonal pair slice
 
 
 class EngineError(RuntimeError):
@@ -91,6 +95,20 @@ def load_library():
     L.atrip_b200_host_tuples.restype = C.c_int64
     L.atrip_b200_host_slice_owner.argtypes = [C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int32]
     L.atrip_b200_host_slice_owner.restype = C.c_int32
+    _ip = C.POINTER(C.c_int64)
+    L.atrip_b200_host_slice_slot.argtypes = [C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int32, _ip]
+    L.atrip_b200_host_slice_slot.restype = C.c_int32
+    L.atrip_b200_host_local_slot.argtypes = [C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32]
+    L.atrip_b200_host_local_slot.restype = C.c_int64
+    L.atrip_b200_host_shard_sizes.argtypes = [C.c_int64, C.c_int32, C.c_int32, _ip]
+    L.atrip_b200_host_plan_batch.argtypes = [C.c_int64, C.c_int32, C.c_int32, _up, C.c_int64, _ip,
+                                             C.POINTER(C.c_int32), _ip, C.c_int64]
+    L.atrip_b200_host_plan_batch.restype = C.c_int64
+    L.atrip_b200_host_cache_need.argtypes = [C.c_int64, C.c_int32, C.c_int32, _up, C.c_int64, C.c_int64, _ip]
+    L.atrip_b200_comm_unique_id.argtypes = [C.c_void_p]
+    L.atrip_b200_comm_init.argtypes = [ctx, C.c_void_p]
+    L.atrip_b200_allreduce.argtypes = [ctx, _dp, C.c_int32]
+    L.atrip_b200_last_exchange.argtypes = [ctx, _dp]
     L.atrip_b200_measure_dmma_peak.argtypes = [C.c_int32, _dp]
     L.atrip_b200_synth_to_host.argtypes = [C.c_int32, C.c_uint64, C.c_int32, C.c_double, C.c_uint64, C.c_uint64, _dp]
     _lib = L
@@ -139,6 +157,63 @@ def host_tuples(distribution, Nv, rank=0, nranks=1, pad=True):
 
 def slice_owner(kind, x, y, Nv, nranks):
     return load_library().atrip_b200_host_slice_owner(kind, x, y, Nv, nranks)
+
+
+def slice_slot(kind, x, y, Nv, nranks):
+    """(owner rank, slot in the owner's store) of a slice"""
+    s = C.c_int64(-1)
+    o = load_library().atrip_b200_host_slice_slot(kind, x, y, Nv, nranks, C.byref(s))
+    return o, s.value
+
+
+def local_slot(kind, x, y, Nv, rank, nranks):
+    """slot of a slice in the store of `rank`, or -1"""
+    return load_library().atrip_b200_host_local_slot(kind, x, y, Nv, rank, nranks)
+
+
+def shard_sizes(Nv, rank, nranks):
+    """owned slots (AX, BY, VIJ) of one rank"""
+    L = load_library()
+    out = (C.c_int64 * 3)()
+    if L.atrip_b200_host_shard_sizes(Nv, rank, nranks, out) != 0:
+        raise EngineError(L.atrip_b200_last_error().decode())
+    return tuple(out)
+
+
+def plan_batch(Nv, rank, nranks, abc, cache_base):
+    """host fetch schedule of one batch: (recs [n,16] int32, ranges [m,5] int64 =
+    peer, store, first slot at owner, count, first cache slot in the region)"""
+    L = load_library()
+    abc = np.ascontiguousarray(abc, dtype=np.uint64).reshape(-1, 3)
+    n = len(abc)
+    base = (C.c_int64 * 3)(*[int(b) for b in cache_base])
+    recs = np.zeros((n, 16), dtype=np.int32)
+    cap = 12 * max(n, 1)
+    ranges = np.zeros((cap, 5), dtype=np.int64)
+    m = L.atrip_b200_host_plan_batch(Nv, rank, nranks, abc.ctypes.data_as(_up), n, base,
+                                     recs.ctypes.data_as(C.POINTER(C.c_int32)),
+                                     ranges.ctypes.data_as(C.POINTER(C.c_int64)), cap)
+    if m < 0:
+        raise EngineError(L.atrip_b200_last_error().decode())
+    return recs, ranges[:m]
+
+
+def cache_need(Nv, rank, nranks, abc, batch):
+    L = load_library()
+    abc = np.ascontiguousarray(abc, dtype=np.uint64).reshape(-1, 3)
+    out = (C.c_int64 * 3)()
+    if L.atrip_b200_host_cache_need(Nv, rank, nranks, abc.ctypes.data_as(_up), len(abc), batch, out) != 0:
+        raise EngineError(L.atrip_b200_last_error().decode())
+    return tuple(out)
+
+
+def comm_unique_id():
+    """128-byte NCCL unique id (rank 0 creates it, the host ships it to the other ranks)"""
+    L = load_library()
+    buf = C.create_string_buffer(128)
+    if L.atrip_b200_comm_unique_id(buf) != 0:
+        raise EngineError(L.atrip_b200_last_error().decode())
+    return buf.raw
 
 
 def _ptr(a):
@@ -245,6 +320,21 @@ class Engine:
         out = np.empty(n)
         self._ck(self.L.atrip_b200_read_slice(self.ctx, kind, x, y, _ptr(out)))
         return out
+
+    # ---- multi-GPU
+    def comm_init(self, unique_id):
+        assert len(unique_id) == 128
+        self._ck(self.L.atrip_b200_comm_init(self.ctx, C.create_string_buffer(bytes(unique_id), 128)))
+
+    def allreduce(self, vals):
+        a = np.ascontiguousarray(vals, dtype=np.float64)
+        self._ck(self.L.atrip_b200_allreduce(self.ctx, _ptr(a), len(a)))
+        return a
+
+    def last_exchange(self):
+        out = (C.c_double * 2)()
+        self.L.atrip_b200_last_exchange(self.ctx, out)
+        return dict(bytes=out[0], messages=int(out[1]))
 
     def last_timing(self):
         out = (C.c_double * 6)()

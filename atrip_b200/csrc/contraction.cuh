@@ -27,10 +27,18 @@
 //                    and stores its C fragments straight to the class cube in HBM/L2.
 #pragma once
 #include "common.cuh"
+#include "schedule.hpp"
 
 namespace ab {
 
 constexpr int MAX_STAGES = 12;
+
+// tensor maps of the owned stores and of the fetch caches (same layouts; a rank that stores
+// everything passes the owned maps twice)
+struct ContractMaps {
+  CUtensorMap A, AT, B;     // owned AX (plain / rows transposed), owned BY
+  CUtensorMap Ac, ATc, Bc;  // cache AX (plain / transposed), cache BY
+};
 
 struct ContractParams {
   int No, Nv, Kp;
@@ -43,10 +51,9 @@ struct ContractParams {
   int brows;    // rows of the B TMA box (min(NI*8, No))
   int nstages;
   int ntuples;
-  const int4 *tuples;  // (a, b, c, -) of the batch
-  const int *xtab;     // virtual index x -> slot in the AX store
-  const int *btab;     // pair index (y + z Nv, or Nv^2 + y for the transposed diagonal) -> BY slot
-  double *R;           // [ntuples][3][No^3] class cubes C_k, C_j, C_i
+  int ownedA, ownedB;      // slots >= owned address the cache maps (schedule.hpp)
+  const TupleRec *recs;    // the batch: tuple + store slots of its slices (built on the host)
+  double *R;               // [ntuples][3][No^3] class cubes C_k, C_j, C_i
 };
 
 __host__ __device__ inline size_t contract_stage_bytes(int arows, int NI) {
@@ -55,8 +62,7 @@ __host__ __device__ inline size_t contract_stage_bytes(int arows, int NI) {
 
 template <int MI, int NI, int MAXT>
 __global__ void __launch_bounds__(MAXT, 1)
-contract_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAT,
-                const __grid_constant__ CUtensorMap tmB, const ContractParams P) {
+contract_kernel(const __grid_constant__ ContractMaps M, const ContractParams P) {
   extern __shared__ unsigned char smem_raw[];
   __shared__ uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES];
 
@@ -78,9 +84,9 @@ contract_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       mbar_init(&empty_bar[s], nwarps);
     }
     fence_barrier_init();
-    tma_prefetch_desc(&tmA);
-    tma_prefetch_desc(&tmAT);
-    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&M.A);
+    tma_prefetch_desc(&M.AT);
+    tma_prefetch_desc(&M.B);
   }
   fence_proxy_async();
   __syncthreads();
@@ -95,35 +101,32 @@ contract_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // ------------------------------------------------------------------ producer
     if (lane == 0) {
       const uint32_t tx = (uint32_t)((P.tu * P.tv + P.brows) * 128);
-      const int NvNv = P.Nv * P.Nv;
       for (long long item = blockIdx.x; item < nitems; item += gridDim.x) {
         const int tup = (int)(item / per_tuple);
         int rem = (int)(item - (long long)tup * per_tuple);
         const int cls = rem / (P.mtiles * P.ntiles);
         rem -= cls * P.mtiles * P.ntiles;
         const int mt = rem / P.ntiles, nt = rem - mt * P.ntiles;
-        const int4 abc = P.tuples[tup];
-        if (abc.x == 0 && abc.y == 0 && abc.z == 0) continue;  // FAKE_TUPLE (Tuples.hpp:43)
-        const int a = abc.x, b = abc.y, c = abc.z;
-        // operands per class: {x plain, (y,z) of its B, transposed-hole flag}, {x transposed, ...}
-        int xs[2], ys[2], zs[2], fs[2];
-        if (cls == 0) { xs[0] = a; ys[0] = b; zs[0] = c; fs[0] = 0; xs[1] = b; ys[1] = a; zs[1] = c; fs[1] = 0; }
-        else if (cls == 1) { xs[0] = a; ys[0] = c; zs[0] = b; fs[0] = 1; xs[1] = c; ys[1] = a; zs[1] = b; fs[1] = 0; }
-        else { xs[0] = b; ys[0] = c; zs[0] = a; fs[0] = 1; xs[1] = c; ys[1] = b; zs[1] = a; fs[1] = 1; }
+        const TupleRec *rec = P.recs + tup;
+        if (rec->fake) continue;  // FAKE_TUPLE (Tuples.hpp:43)
+        // operands per class: piece 0 = A_x plain, piece 1 = A_x with (p,q) exchanged;
+        //   class 0: A_a B_bc + A_b^T B_ac   class 1: A_a B_cb' + A_c^T B_ab   class 2: A_b B_ca' + A_c^T B_ba'
+        // rec->by is stored in exactly this (class, piece) order
 #pragma unroll
         for (int piece = 0; piece < 2; piece++) {
-          const int xslot = P.xtab[xs[piece]];
-          const int bidx = (ys[piece] == zs[piece] && fs[piece]) ? NvNv + ys[piece]
-                                                                : ys[piece] + zs[piece] * P.Nv;
-          const int bslot = P.btab[bidx];
-          const CUtensorMap *tm = piece ? &tmAT : &tmA;
+          int xslot = rec->ax[cls == 0 ? piece : (cls == 1 ? 2 * piece : 1 + piece)];
+          int bslot = rec->by[2 * cls + piece];
+          const CUtensorMap *tm, *tmb = &M.B;
+          if (xslot >= P.ownedA) { xslot -= P.ownedA; tm = piece ? &M.ATc : &M.Ac; }
+          else tm = piece ? &M.AT : &M.A;
+          if (bslot >= P.ownedB) { bslot -= P.ownedB; tmb = &M.Bc; }
           const int u0 = (mt % P.utiles) * P.tu, v0 = (mt / P.utiles) * P.tv;
           for (int kc = 0; kc < P.nk; kc++) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             unsigned char *sb = base + (size_t)stage * stage_bytes;
             mbar_expect_tx(&full_bar[stage], tx);
             tma_load_4d(sb, tm, &full_bar[stage], kc * KC, u0, v0, xslot);
-            tma_load_3d(sb + (size_t)P.arows * 128, &tmB, &full_bar[stage], kc * KC, nt * NI * 8, bslot);
+            tma_load_3d(sb + (size_t)P.arows * 128, tmb, &full_bar[stage], kc * KC, nt * NI * 8, bslot);
             if (++stage == P.nstages) { stage = 0; phase ^= 1; }
           }
         }
@@ -149,8 +152,7 @@ contract_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int cls = rem / (P.mtiles * P.ntiles);
     rem -= cls * P.mtiles * P.ntiles;
     const int mt = rem / P.ntiles, nt = rem - mt * P.ntiles;
-    const int4 abc = P.tuples[tup];
-    if (abc.x == 0 && abc.y == 0 && abc.z == 0) continue;
+    if (P.recs[tup].fake) continue;
 
     double acc[MI][NI][2];
 #pragma unroll

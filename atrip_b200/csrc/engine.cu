@@ -11,9 +11,11 @@
 #include <vector>
 
 #include "../../include/atrip_b200.h"
+#include "comm.hpp"
 #include "common.cuh"
 #include "contraction.cuh"
 #include "reduction.cuh"
+#include "schedule.hpp"
 #include "stores.cuh"
 #include "tuples.hpp"
 
@@ -154,53 +156,75 @@ T *dalloc(size_t n) {
 
 }  // namespace
 
+constexpr int REC_RING = 4;  // batches the host may run ahead of the device
+
 struct atrip_b200_ctx {
   atrip_b200_config cfg{};
   int No = 0, Nv = 0, Kp = 0;
   int nsm = 0;
   size_t smem_limit = 0;
-  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  cudaStream_t stream = nullptr, xstream = nullptr;  // compute; slice exchange (side stream)
   cudaEvent_t ev[6]{};
 
-  // stores
-  size_t nX = 0, nB = 0, nV = 0;
+  // stores: owned slices in the layouts of stores.cuh, slot numbering of schedule.hpp
+  ShardMap map;                // storage sharding (replica: n = 1)
+  int64_t owned[3] = {0, 0, 0};  // owned slots per kind (KA, KB, KV)
   double *AX = nullptr, *BY = nullptr, *VIJ = nullptr;
   double *AXJ = nullptr, *BYJ = nullptr;  // (cT): J tensors in the same layouts
   double *eps_i = nullptr, *eps_a = nullptr, *Tai = nullptr;
-  int *xtab = nullptr, *btab = nullptr, *vtab = nullptr;
+  int *xtab = nullptr, *btab = nullptr, *vtab = nullptr;  // global id -> owned slot or -1 (ingest)
   int *xlist = nullptr, *ylist = nullptr, *zlist = nullptr, *tflag = nullptr, *vy = nullptr, *vz = nullptr;
   bool have_J = false;
 
+  // fetch caches (sharded stores only): two regions of cap[kind] slots, used by alternate batches
+  int64_t cap[3] = {0, 0, 0};
+  double *cA = nullptr, *cB = nullptr, *cV = nullptr, *cAJ = nullptr, *cBJ = nullptr;
+
   // tuples
   std::vector<Tuple> tuples;
-  int4 *d_tuples = nullptr;
-  size_t d_tuples_cap = 0;
 
   // work buffers
   int batch = 0;
   double *R = nullptr, *RJ = nullptr, *e_tuple = nullptr, *d_total = nullptr;
-  int4 *dbg_tuple = nullptr;
+  TupleRec *h_recs = nullptr, *d_recs = nullptr;  // [REC_RING][batch]
+  cudaEvent_t rec_ev[REC_RING]{};
+  uint64_t rec_uses = 0;
 
   // kernel plan
   ContractPlan plan;
-  CUtensorMap tmA, tmAT, tmB, tmAJ, tmATJ, tmBJ;
+  ContractMaps maps, mapsJ;
+
+  // slice exchange
+  ncclComm_t comm = nullptr;
+  size_t req_cap = 0;                                     // ints per request list
+  int32_t *h_req_send = nullptr, *h_req_recv = nullptr;   // pinned [2][nranks][req_cap]
+  int32_t *d_req_send = nullptr, *d_req_recv = nullptr;
+  cudaEvent_t xdone[4]{}, cdone[4]{};
+  double *d_reduce = nullptr;                             // all-reduce scratch
+  double exch_bytes = 0, exch_msgs = 0;                   // of the last run (received)
 
   // staging for ingest
   double *h_stage[2] = {nullptr, nullptr}, *d_stage[2] = {nullptr, nullptr};
   size_t stage_elems = 0;
   cudaEvent_t stage_ev[2]{};
 
-  double timing[6] = {0, 0, 0, 0, 0, 0};
+  double timing[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
 
 namespace {
 
 StoreDims dims_of(const atrip_b200_ctx *c) { return StoreDims{c->No, c->Nv, c->Kp}; }
 
-void build_maps(atrip_b200_ctx *c, double *AX, double *BY, CUtensorMap *tA, CUtensorMap *tAT, CUtensorMap *tB) {
+size_t slice_elems(const atrip_b200_ctx *c, int kind) {
+  const size_t No = c->No, Kp = c->Kp;
+  return kind == KA ? No * No * Kp : (kind == KB ? No * Kp : No * No);
+}
+
+void build_maps(atrip_b200_ctx *c, double *AX, uint64_t nA, double *BY, uint64_t nB, CUtensorMap *tA,
+                CUtensorMap *tAT, CUtensorMap *tB) {
   const uint64_t No = c->No, Kp = c->Kp;
   {
-    const uint64_t dims[4] = {Kp, No, No, c->nX};
+    const uint64_t dims[4] = {Kp, No, No, std::max<uint64_t>(nA, 1)};
     const uint64_t strP[3] = {Kp * 8, No * Kp * 8, No * No * Kp * 8};
     const uint64_t strT[3] = {No * Kp * 8, Kp * 8, No * No * Kp * 8};
     const uint32_t box[4] = {KC, (uint32_t)c->plan.tu, (uint32_t)c->plan.tv, 1};
@@ -208,11 +232,46 @@ void build_maps(atrip_b200_ctx *c, double *AX, double *BY, CUtensorMap *tA, CUte
     make_map(tAT, AX, 4, dims, strT, box);
   }
   {
-    const uint64_t dims[3] = {Kp, No, c->nB};
+    const uint64_t dims[3] = {Kp, No, std::max<uint64_t>(nB, 1)};
     const uint64_t str[2] = {Kp * 8, No * Kp * 8};
     const uint32_t box[3] = {KC, (uint32_t)c->plan.brows, 1};
     make_map(tB, BY, 3, dims, str, box);
   }
+}
+
+// (re)build all tensor maps: owned stores, and the fetch caches when there are any
+void build_all_maps(atrip_b200_ctx *c) {
+  build_maps(c, c->AX, c->owned[KA], c->BY, c->owned[KB], &c->maps.A, &c->maps.AT, &c->maps.B);
+  if (c->cA) build_maps(c, c->cA, 2 * c->cap[KA], c->cB, 2 * c->cap[KB], &c->maps.Ac, &c->maps.ATc, &c->maps.Bc);
+  else { c->maps.Ac = c->maps.A; c->maps.ATc = c->maps.AT; c->maps.Bc = c->maps.B; }
+  if (c->cfg.with_J) {
+    build_maps(c, c->AXJ, c->owned[KA], c->BYJ, c->owned[KB], &c->mapsJ.A, &c->mapsJ.AT, &c->mapsJ.B);
+    if (c->cAJ) build_maps(c, c->cAJ, 2 * c->cap[KA], c->cBJ, 2 * c->cap[KB], &c->mapsJ.Ac, &c->mapsJ.ATc, &c->mapsJ.Bc);
+    else { c->mapsJ.Ac = c->mapsJ.A; c->mapsJ.ATc = c->mapsJ.AT; c->mapsJ.Bc = c->mapsJ.B; }
+  }
+}
+
+bool sharded(const atrip_b200_ctx *c) { return c->map.n > 1; }
+
+// fetch caches sized for the current tuple list (schedule.hpp: cache_need); grown on demand
+void ensure_caches(atrip_b200_ctx *c, const int64_t need[3]) {
+  if (!sharded(c)) return;
+  // a debug tuple (12 slices, all remote in the worst case) must always fit
+  const int64_t want[3] = {std::max<int64_t>(need[KA], 3), std::max<int64_t>(need[KB], 6), std::max<int64_t>(need[KV], 3)};
+  if (c->cA && want[KA] <= c->cap[KA] && want[KB] <= c->cap[KB] && want[KV] <= c->cap[KV]) return;
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  CUDA_OK(cudaStreamSynchronize(c->xstream));
+  for (double **p : {&c->cA, &c->cB, &c->cV, &c->cAJ, &c->cBJ})
+    if (*p) { cudaFree(*p); *p = nullptr; }
+  for (int k = 0; k < 3; k++) c->cap[k] = std::max(c->cap[k], want[k]);
+  c->cA = dalloc<double>(2 * c->cap[KA] * slice_elems(c, KA));
+  c->cB = dalloc<double>(2 * c->cap[KB] * slice_elems(c, KB));
+  c->cV = dalloc<double>(2 * c->cap[KV] * slice_elems(c, KV));
+  if (c->cfg.with_J) {
+    c->cAJ = dalloc<double>(2 * c->cap[KA] * slice_elems(c, KA));
+    c->cBJ = dalloc<double>(2 * c->cap[KB] * slice_elems(c, KB));
+  }
+  build_all_maps(c);
 }
 
 void ensure_stage(atrip_b200_ctx *c, size_t elems) {
@@ -258,7 +317,7 @@ void stream_chunks(atrip_b200_ctx *c, const double *host, size_t nchunks, size_t
   CUDA_OK(cudaStreamSynchronize(c->stream));
 }
 
-void launch_contract(atrip_b200_ctx *c, const int4 *d_tuples, int ntuples, bool useJ) {
+void launch_contract(atrip_b200_ctx *c, const TupleRec *d_recs, int ntuples, bool useJ) {
   ContractParams P;
   P.No = c->No;
   P.Nv = c->Nv;
@@ -273,31 +332,31 @@ void launch_contract(atrip_b200_ctx *c, const int4 *d_tuples, int ntuples, bool 
   P.brows = c->plan.brows;
   P.nstages = c->plan.nstages;
   P.ntuples = ntuples;
-  P.tuples = d_tuples;
-  P.xtab = c->xtab;
-  P.btab = c->btab;
+  P.ownedA = (int)c->owned[KA];
+  P.ownedB = (int)c->owned[KB];
+  P.recs = d_recs;
   P.R = useJ ? c->RJ : c->R;
   const long long nitems = 3LL * P.mtiles * P.ntiles * ntuples;
   const int grid = (int)std::min<long long>(c->nsm, nitems);
   if (grid <= 0) return;
-  void *args[4] = {useJ ? (void *)&c->tmAJ : (void *)&c->tmA, useJ ? (void *)&c->tmATJ : (void *)&c->tmAT,
-                   useJ ? (void *)&c->tmBJ : (void *)&c->tmB, (void *)&P};
+  void *args[2] = {useJ ? (void *)&c->mapsJ : (void *)&c->maps, (void *)&P};
   CUDA_OK(cudaLaunchKernel(c->plan.k->fn, dim3(grid), dim3((c->plan.nw + 1) * 32), args, c->plan.smem, c->stream));
 }
 
-ReduceParams reduce_params(atrip_b200_ctx *c, const int4 *d_tuples, int ntuples, bool ct) {
+ReduceParams reduce_params(atrip_b200_ctx *c, const TupleRec *d_recs, int ntuples, bool ct) {
   ReduceParams P;
   P.No = c->No;
   P.Nv = c->Nv;
   P.ntuples = ntuples;
-  P.tuples = d_tuples;
+  P.recs = d_recs;
   P.R = ct ? c->RJ : c->R;
   P.RZ = c->R;
   P.eps_i = c->eps_i;
   P.eps_a = c->eps_a;
   P.Tai = c->Tai;
   P.VIJ = c->VIJ;
-  P.vtab = c->vtab;
+  P.VIJc = c->cV ? c->cV : c->VIJ;
+  P.ownedV = (int)c->owned[KV];
   P.e_tuple = c->e_tuple;
   // enough CTAs to fill the GPU a few times over even when a batch has few tuples (large No)
   const int nb = (c->No + RT - 1) / RT, orbits = nb * (nb + 1) * (nb + 2) / 6;
@@ -305,9 +364,9 @@ ReduceParams reduce_params(atrip_b200_ctx *c, const int4 *d_tuples, int ntuples,
   return P;
 }
 
-void launch_reduce(atrip_b200_ctx *c, const int4 *d_tuples, int ntuples, bool ct, double *total) {
+void launch_reduce(atrip_b200_ctx *c, const TupleRec *d_recs, int ntuples, bool ct, double *total) {
   if (ntuples <= 0) return;
-  ReduceParams P = reduce_params(c, d_tuples, ntuples, ct);
+  ReduceParams P = reduce_params(c, d_recs, ntuples, ct);
   const size_t smem = reduce_smem_bytes(c->No, ct);
   const dim3 grid(ntuples, P.nsplit);
   if (ct) reduce_kernel<true><<<grid, REDUCE_THREADS, smem, c->stream>>>(P);
@@ -317,16 +376,12 @@ void launch_reduce(atrip_b200_ctx *c, const int4 *d_tuples, int ntuples, bool ct
   CUDA_OK(cudaGetLastError());
 }
 
-void upload_tuples(atrip_b200_ctx *c) {
-  const size_t n = c->tuples.size();
-  if (n > c->d_tuples_cap) {
-    if (c->d_tuples) cudaFree(c->d_tuples);
-    c->d_tuples = dalloc<int4>(n);
-    c->d_tuples_cap = n;
-  }
-  std::vector<int4> h(n);
-  for (size_t i = 0; i < n; i++) h[i] = make_int4((int)c->tuples[i][0], (int)c->tuples[i][1], (int)c->tuples[i][2], 0);
-  CUDA_OK(cudaMemcpy(c->d_tuples, h.data(), n * sizeof(int4), cudaMemcpyHostToDevice));
+template <typename T>
+int *upload_ints(const std::vector<T> &h) {
+  std::vector<int> v(h.begin(), h.end());
+  int *d = dalloc<int>(v.size());
+  CUDA_OK(cudaMemcpy(d, v.data(), v.size() * sizeof(int), cudaMemcpyHostToDevice));
+  return d;
 }
 
 void create_impl(atrip_b200_ctx *c) {
@@ -351,8 +406,11 @@ void create_impl(atrip_b200_ctx *c) {
   c->Nv = (int)cfg.Nv;
   c->Kp = (int)((cfg.No + cfg.Nv + KC - 1) / KC * KC);
   CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-  CUDA_OK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  CUDA_OK(cudaStreamCreateWithFlags(&c->xstream, cudaStreamNonBlocking));
   for (auto &ev : c->ev) CUDA_OK(cudaEventCreate(&ev));
+  for (auto &ev : c->rec_ev) CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  for (auto &ev : c->xdone) CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  for (auto &ev : c->cdone) CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
 
   c->plan = plan_contraction(c->No, c->smem_limit);
   REQUIRE(c->plan.k, "no contraction kernel variant fits this No");
@@ -362,51 +420,54 @@ void create_impl(atrip_b200_ctx *c) {
   CUDA_OK(cudaFuncSetAttribute((const void *)reduce_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)reduce_smem_bytes(c->No, true)));
 
-  // ---- slot tables.  resident: every slice lives here.
-  REQUIRE(cfg.resident || cfg.nranks == 1, "non-resident (owned slices + fetch cache) stores: not in this build");
-  const size_t Nv = c->Nv, NvNv = Nv * Nv;
-  std::vector<int> xtab(Nv), xlist(Nv);
-  for (size_t x = 0; x < Nv; x++) xtab[x] = xlist[x] = (int)x;
-  c->nX = Nv;
-  std::vector<int> btab(NvNv + Nv), yl(NvNv + Nv), zl(NvNv + Nv), tf(NvNv + Nv, 0);
-  for (size_t z = 0; z < Nv; z++)
-    for (size_t y = 0; y < Nv; y++) {
-      btab[y + z * Nv] = (int)(y + z * Nv);
-      yl[y + z * Nv] = (int)y;
-      zl[y + z * Nv] = (int)z;
-    }
-  for (size_t y = 0; y < Nv; y++) {
-    btab[NvNv + y] = (int)(NvNv + y);
-    yl[NvNv + y] = zl[NvNv + y] = (int)y;
-    tf[NvNv + y] = 1;
+  // ---- which slices live here: everything (replica) or the slices this rank owns
+  const int sn = (cfg.resident || cfg.nranks == 1) ? 1 : cfg.nranks;
+  c->map = ShardMap(cfg.Nv, sn, sn == 1 ? 0 : cfg.rank);
+  const ShardMap &m = c->map;
+  for (int k = 0; k < 3; k++) c->owned[k] = m.owned(k, m.me);
+  REQUIRE(c->owned[KB] < (1LL << 31) && c->owned[KV] < (1LL << 31), "too many slots for 32-bit slot numbers");
+  const int64_t Nv = c->Nv, NvNv = Nv * Nv;
+  {
+    std::vector<int> xtab((size_t)Nv, -1), xlist((size_t)c->owned[KA], 0);
+    for (int64_t x = 0; x < Nv; x++)
+      if (m.ownerA(x) == m.me) {
+        xtab[(size_t)x] = (int)m.slotA(x);
+        xlist[(size_t)m.slotA(x)] = (int)x;
+      }
+    std::vector<int> btab((size_t)(NvNv + Nv), -1), yl((size_t)c->owned[KB], 0), zl((size_t)c->owned[KB], 0),
+        tf((size_t)c->owned[KB], 0);
+    for (int64_t id = 0; id < NvNv + Nv; id++)
+      if (m.ownerB(id) == m.me) {
+        const int64_t s = m.slotB(id);
+        btab[(size_t)id] = (int)s;
+        yl[(size_t)s] = (int)(id < NvNv ? id % Nv : id - NvNv);
+        zl[(size_t)s] = (int)(id < NvNv ? id / Nv : id - NvNv);
+        tf[(size_t)s] = id >= NvNv;
+      }
+    std::vector<int> vtab((size_t)NvNv, -1), vy((size_t)c->owned[KV], 0), vz((size_t)c->owned[KV], 0);
+    for (int64_t z = 0; z < Nv; z++)
+      for (int64_t y = 0; y <= z; y++) {
+        const int64_t s = m.localV(y, z);
+        if (s < 0) continue;
+        vtab[(size_t)(y + z * Nv)] = (int)s;
+        vy[(size_t)s] = (int)y;
+        vz[(size_t)s] = (int)z;
+      }
+    c->xtab = upload_ints(xtab);
+    c->xlist = upload_ints(xlist);
+    c->btab = upload_ints(btab);
+    c->ylist = upload_ints(yl);
+    c->zlist = upload_ints(zl);
+    c->tflag = upload_ints(tf);
+    c->vtab = upload_ints(vtab);
+    c->vy = upload_ints(vy);
+    c->vz = upload_ints(vz);
   }
-  c->nB = NvNv + Nv;
-  std::vector<int> vtab(NvNv, -1), vy, vz;
-  for (size_t z = 0; z < Nv; z++)
-    for (size_t y = 0; y <= z; y++) {
-      vtab[y + z * Nv] = (int)vy.size();
-      vy.push_back((int)y);
-      vz.push_back((int)z);
-    }
-  c->nV = vy.size();
-  auto up = [&](const std::vector<int> &h) {
-    int *d = dalloc<int>(h.size());
-    CUDA_OK(cudaMemcpy(d, h.data(), h.size() * sizeof(int), cudaMemcpyHostToDevice));
-    return d;
-  };
-  c->xtab = up(xtab);
-  c->xlist = up(xlist);
-  c->btab = up(btab);
-  c->ylist = up(yl);
-  c->zlist = up(zl);
-  c->tflag = up(tf);
-  c->vtab = up(vtab);
-  c->vy = up(vy);
-  c->vz = up(vz);
 
   // ---- stores
-  const size_t No = c->No, Kp = c->Kp;
-  const size_t axn = c->nX * No * No * Kp, byn = c->nB * No * Kp, vn = c->nV * No * No;
+  const size_t No = c->No;
+  const size_t axn = c->owned[KA] * slice_elems(c, KA), byn = c->owned[KB] * slice_elems(c, KB),
+               vn = c->owned[KV] * slice_elems(c, KV);
   c->AX = dalloc<double>(axn);
   c->BY = dalloc<double>(byn);
   c->VIJ = dalloc<double>(vn);
@@ -438,10 +499,21 @@ void create_impl(atrip_b200_ctx *c) {
   if (cfg.with_J) c->RJ = dalloc<double>(cube3 * c->batch);
   c->e_tuple = dalloc<double>((size_t)c->batch * 64);
   c->d_total = dalloc<double>(2);
-  c->dbg_tuple = dalloc<int4>(1);
+  c->d_reduce = dalloc<double>(16);
+  CUDA_OK(cudaMallocHost(&c->h_recs, sizeof(TupleRec) * REC_RING * c->batch));
+  c->d_recs = dalloc<TupleRec>((size_t)REC_RING * c->batch);
 
-  build_maps(c, c->AX, c->BY, &c->tmA, &c->tmAT, &c->tmB);
-  if (cfg.with_J) build_maps(c, c->AXJ, c->BYJ, &c->tmAJ, &c->tmATJ, &c->tmBJ);
+  if (sharded(c)) {
+    c->req_cap = request_capacity_ints((size_t)c->batch);
+    const size_t n = 2 * (size_t)cfg.nranks * c->req_cap;
+    CUDA_OK(cudaMallocHost(&c->h_req_send, n * sizeof(int32_t)));
+    CUDA_OK(cudaMallocHost(&c->h_req_recv, n * sizeof(int32_t)));
+    c->d_req_send = dalloc<int32_t>(n);
+    c->d_req_recv = dalloc<int32_t>(n);
+    const int64_t none[3] = {0, 0, 0};
+    ensure_caches(c, none);
+  }
+  build_all_maps(c);
   CUDA_OK(cudaStreamSynchronize(c->stream));
 }
 
@@ -449,19 +521,29 @@ void destroy_impl(atrip_b200_ctx *c) {
   if (!c) return;
   cudaSetDevice(c->cfg.device);
   if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->xstream) cudaStreamSynchronize(c->xstream);
+  if (c->comm && nccl().ok) nccl().CommDestroy(c->comm);
   void *ptrs[] = {c->AX, c->BY, c->VIJ, c->AXJ, c->BYJ, c->eps_i, c->eps_a, c->Tai, c->xtab, c->btab,
-                  c->vtab, c->xlist, c->ylist, c->zlist, c->tflag, c->vy, c->vz, c->d_tuples, c->R, c->RJ,
-                  c->e_tuple, c->d_total, c->dbg_tuple, c->d_stage[0], c->d_stage[1]};
+                  c->vtab, c->xlist, c->ylist, c->zlist, c->tflag, c->vy, c->vz, c->R, c->RJ,
+                  c->e_tuple, c->d_total, c->d_reduce, c->d_recs, c->d_stage[0], c->d_stage[1],
+                  c->cA, c->cB, c->cV, c->cAJ, c->cBJ, c->d_req_send, c->d_req_recv};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   for (auto *h : c->h_stage)
     if (h) cudaFreeHost(h);
-  for (auto &ev : c->ev)
-    if (ev) cudaEventDestroy(ev);
-  for (auto &ev : c->stage_ev)
-    if (ev) cudaEventDestroy(ev);
+  for (void *h : {(void *)c->h_recs, (void *)c->h_req_send, (void *)c->h_req_recv})
+    if (h) cudaFreeHost(h);
+  auto kill = [](cudaEvent_t *evs, int n) {
+    for (int i = 0; i < n; i++)
+      if (evs[i]) cudaEventDestroy(evs[i]);
+  };
+  kill(c->ev, 6);
+  kill(c->stage_ev, 2);
+  kill(c->rec_ev, REC_RING);
+  kill(c->xdone, 4);
+  kill(c->cdone, 4);
   if (c->stream) cudaStreamDestroy(c->stream);
-  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  if (c->xstream) cudaStreamDestroy(c->xstream);
   delete c;
 }
 
@@ -469,20 +551,21 @@ int grid_for(size_t n, int nsm) { return (int)std::min<size_t>((n + 255) / 256, 
 
 void fill_impl(atrip_b200_ctx *c, uint64_t seed, double scale) {
   const StoreDims d = dims_of(c);
-  const size_t No = c->No, Kp = c->Kp;
+  const size_t No = c->No;
+  const size_t nX = c->owned[KA], nB = c->owned[KB], nV = c->owned[KV];
   fill_small_kernel<<<grid_for(No * (size_t)c->Nv, c->nsm), 256, 0, c->stream>>>(
       c->eps_i, c->eps_a, c->Tai, d, synth_key(seed, T_EPS_I), synth_key(seed, T_EPS_A), synth_key(seed, T_TAI), scale);
-  fill_AX_kernel<<<grid_for(c->nX * No * No * Kp, c->nsm), 256, 0, c->stream>>>(
-      c->AX, d, c->xlist, (int)c->nX, synth_key(seed, T_TABIJ), synth_key(seed, T_VIJKA), scale);
-  fill_BY_kernel<<<grid_for(c->nB * No * Kp, c->nsm), 256, 0, c->stream>>>(
-      c->BY, d, c->ylist, c->zlist, c->tflag, c->nB, synth_key(seed, T_VABCI), synth_key(seed, T_TABIJ), scale);
-  fill_VIJ_kernel<<<grid_for(c->nV * No * No, c->nsm), 256, 0, c->stream>>>(c->VIJ, d, c->vy, c->vz, c->nV,
-                                                                          synth_key(seed, T_VABIJ), scale);
+  fill_AX_kernel<<<grid_for(nX * slice_elems(c, KA), c->nsm), 256, 0, c->stream>>>(
+      c->AX, d, c->xlist, (int)nX, synth_key(seed, T_TABIJ), synth_key(seed, T_VIJKA), scale);
+  fill_BY_kernel<<<grid_for(nB * slice_elems(c, KB), c->nsm), 256, 0, c->stream>>>(
+      c->BY, d, c->ylist, c->zlist, c->tflag, nB, synth_key(seed, T_VABCI), synth_key(seed, T_TABIJ), scale);
+  fill_VIJ_kernel<<<grid_for(nV * slice_elems(c, KV), c->nsm), 256, 0, c->stream>>>(c->VIJ, d, c->vy, c->vz, nV,
+                                                                                   synth_key(seed, T_VABIJ), scale);
   if (c->cfg.with_J) {
-    fill_AX_kernel<<<grid_for(c->nX * No * No * Kp, c->nsm), 256, 0, c->stream>>>(
-        c->AXJ, d, c->xlist, (int)c->nX, synth_key(seed, T_TABIJ), synth_key(seed, T_JIJKA), scale);
-    fill_BY_kernel<<<grid_for(c->nB * No * Kp, c->nsm), 256, 0, c->stream>>>(
-        c->BYJ, d, c->ylist, c->zlist, c->tflag, c->nB, synth_key(seed, T_JABCI), synth_key(seed, T_TABIJ), scale);
+    fill_AX_kernel<<<grid_for(nX * slice_elems(c, KA), c->nsm), 256, 0, c->stream>>>(
+        c->AXJ, d, c->xlist, (int)nX, synth_key(seed, T_TABIJ), synth_key(seed, T_JIJKA), scale);
+    fill_BY_kernel<<<grid_for(nB * slice_elems(c, KB), c->nsm), 256, 0, c->stream>>>(
+        c->BYJ, d, c->ylist, c->zlist, c->tflag, nB, synth_key(seed, T_JABCI), synth_key(seed, T_TABIJ), scale);
     c->have_J = true;
   }
   CUDA_OK(cudaGetLastError());
@@ -561,33 +644,157 @@ void load_ppph_impl(atrip_b200_ctx *c, const double *V, double *BY) {
   CUDA_OK(cudaGetLastError());
 }
 
-void run_impl(atrip_b200_ctx *c, int64_t first, int64_t count, double *energy, double *ct_energy) {
-  REQUIRE(first >= 0 && count >= 0 && (size_t)(first + count) <= c->tuples.size(), "tuple range out of bounds");
-  REQUIRE(c->d_tuples != nullptr || count == 0, "no tuple list: call atrip_b200_build_tuples / set_tuples first");
+// ------------------------------------------------------------------ slice exchange (NCCL)
+#define NCCL_OK(expr)                                                                              \
+  do {                                                                                             \
+    ncclResult_t r__ = (expr);                                                                     \
+    if (r__ != ncclSuccess)                                                                        \
+      throw Fail{std::string("NCCL: ") + nccl().GetErrorString(r__) + " in " #expr " (" __FILE__ ":" + \
+                 std::to_string(__LINE__) + ")"};                                                  \
+  } while (0)
+
+int32_t *req_buf(const atrip_b200_ctx *c, int32_t *base, int parity, int peer) {
+  return base + ((size_t)parity * c->cfg.nranks + peer) * c->req_cap;
+}
+
+double *store_of(const atrip_b200_ctx *c, int kind, bool J) {
+  return kind == KA ? (J ? c->AXJ : c->AX) : (kind == KB ? (J ? c->BYJ : c->BY) : c->VIJ);
+}
+double *cache_of(const atrip_b200_ctx *c, int kind, bool J) {
+  return kind == KA ? (J ? c->cAJ : c->cA) : (kind == KB ? (J ? c->cBJ : c->cB) : c->cV);
+}
+
+// One exchange step on the side stream (replaces do_io_phase, Atrip.cxx:461-572, one BATCH at a
+// time): inside one NCCL group
+//   data     for batch `k`:  send the ranges every peer asked of me (peer_req, host copy of the
+//            request lists received one step earlier), receive the ranges of my own plan into
+//            cache region k % 2;
+//   requests for batch k+1:  send my request lists (next != nullptr), receive the peers'.
+// k = -1 is the bootstrap step that only exchanges the request lists of batch 0.
+void exchange_step(atrip_b200_ctx *c, int64_t k, const BatchPlan *mine, const BatchPlan *next) {
+  NcclApi &N = nccl();
+  const int n = c->cfg.nranks, me = c->cfg.rank;
+  const bool J = c->have_J;
+  const int nextpar = (int)((k + 1) & 1), par = (int)(k & 1);
+  if (next) {
+    for (int p = 0; p < n; p++) encode_requests(next->fetch[(size_t)p], req_buf(c, c->h_req_send, nextpar, p));
+    CUDA_OK(cudaMemcpyAsync(req_buf(c, c->d_req_send, nextpar, 0), req_buf(c, c->h_req_send, nextpar, 0),
+                            (size_t)n * c->req_cap * sizeof(int32_t), cudaMemcpyHostToDevice, c->xstream));
+  }
+  NCCL_OK(N.GroupStart());
+  for (int p = 0; p < n; p++) {
+    if (p == me) continue;
+    if (k >= 0) {
+      // what peer p asked of me for its batch k, in its order
+      const int32_t *rq = req_buf(c, c->h_req_recv, par, p);
+      const int nr = rq[0];
+      REQUIRE(nr >= 0 && (size_t)(1 + 3 * (int64_t)nr) <= c->req_cap, "corrupt slice request list");
+      for (int i = 0; i < nr; i++) {
+        const int kind = rq[1 + 3 * i];
+        const int64_t slot = rq[2 + 3 * i], cnt = rq[3 + 3 * i];
+        REQUIRE(kind >= 0 && kind < 3 && slot >= 0 && cnt > 0 && slot + cnt <= c->owned[kind],
+                "peer requested a slice this rank does not own");
+        const size_t el = slice_elems(c, kind);
+        NCCL_OK(N.Send(store_of(c, kind, false) + (size_t)slot * el, (size_t)cnt * el, ncclFloat64, p, c->comm, c->xstream));
+        if (J && kind != KV)
+          NCCL_OK(N.Send(store_of(c, kind, true) + (size_t)slot * el, (size_t)cnt * el, ncclFloat64, p, c->comm, c->xstream));
+      }
+      for (const FetchRange &fr : mine->fetch[(size_t)p]) {
+        const size_t el = slice_elems(c, fr.kind);
+        const size_t dst = (size_t)(par * c->cap[fr.kind] + fr.dst_slot) * el;
+        NCCL_OK(N.Recv(cache_of(c, fr.kind, false) + dst, (size_t)fr.count * el, ncclFloat64, p, c->comm, c->xstream));
+        if (J && fr.kind != KV)
+          NCCL_OK(N.Recv(cache_of(c, fr.kind, true) + dst, (size_t)fr.count * el, ncclFloat64, p, c->comm, c->xstream));
+        c->exch_bytes += (double)fr.count * el * 8 * ((J && fr.kind != KV) ? 2 : 1);
+        c->exch_msgs += 1;
+      }
+    }
+    if (next) {
+      NCCL_OK(N.Send(req_buf(c, c->d_req_send, nextpar, p), c->req_cap, ncclInt32, p, c->comm, c->xstream));
+      NCCL_OK(N.Recv(req_buf(c, c->d_req_recv, nextpar, p), c->req_cap, ncclInt32, p, c->comm, c->xstream));
+    }
+  }
+  NCCL_OK(N.GroupEnd());
+  if (next)
+    CUDA_OK(cudaMemcpyAsync(req_buf(c, c->h_req_recv, nextpar, 0), req_buf(c, c->d_req_recv, nextpar, 0),
+                            (size_t)n * c->req_cap * sizeof(int32_t), cudaMemcpyDeviceToHost, c->xstream));
+}
+
+// Runs the tuples list[0..count) in device batches.  Replaces the main loop, Atrip.cxx:686-1057.
+// Sharded stores: COLLECTIVE -- every rank calls with the same count; slices of batch k+1 travel
+// on the side stream while batch k computes (two cache regions).
+void run_list(atrip_b200_ctx *c, const Tuple *list, int64_t count, double *energy, double *ct_energy) {
   const bool ct = c->have_J;
+  const bool sh = sharded(c);
+  REQUIRE(!sh || c->comm, "sharded stores need atrip_b200_comm_init before running tuples");
+  const int64_t nb = (count + c->batch - 1) / c->batch;
+  auto nt_of = [&](int64_t k) { return (size_t)std::min<int64_t>(c->batch, count - k * c->batch); };
+  auto base_of = [&](int64_t k, int64_t base[3]) {
+    for (int q = 0; q < 3; q++) base[q] = c->owned[q] + (sh ? (k & 1) * c->cap[q] : 0);
+  };
+  BatchPlan plans[3];
+  auto make_plan = [&](int64_t k) {
+    int64_t base[3];
+    base_of(k, base);
+    BatchPlan &pl = plans[k % 3];
+    plan_batch(c->map, list + k * c->batch, nt_of(k), base, pl);
+    for (int q = 0; q < 3; q++)
+      REQUIRE(pl.used[q] <= c->cap[q] || !sh, "fetch cache too small for this batch (tuple list changed without set_tuples?)");
+  };
+  c->exch_bytes = c->exch_msgs = 0;
   CUDA_OK(cudaMemsetAsync(c->d_total, 0, 2 * sizeof(double), c->stream));
-  cudaEvent_t e_begin = c->ev[0], e_end = c->ev[1];
-  // per-kernel events are recorded around the first batches only (they serialise nothing on one
-  // stream, but keep the count small): contraction [2,3], reduction [4,5]
   double ms_contract = 0, ms_reduce = 0;
   int n_contract = 0, n_reduce = 0, sampled = 0;
-  CUDA_OK(cudaEventRecord(e_begin, c->stream));
-  for (int64_t t0 = first; t0 < first + count; t0 += c->batch) {
-    const int nt = (int)std::min<int64_t>(c->batch, first + count - t0);
-    const int4 *tp = c->d_tuples + t0;
+  CUDA_OK(cudaEventRecord(c->ev[0], c->stream));
+  if (nb > 0) make_plan(0);
+  if (sh && nb > 0) {
+    // last run's compute may still read the caches / request buffers: order the side stream after it
+    CUDA_OK(cudaEventRecord(c->cdone[3], c->stream));
+    CUDA_OK(cudaStreamWaitEvent(c->xstream, c->cdone[3], 0));
+    exchange_step(c, -1, nullptr, &plans[0]);
+    CUDA_OK(cudaStreamSynchronize(c->xstream));
+    if (nb > 1) make_plan(1);
+    exchange_step(c, 0, &plans[0], nb > 1 ? &plans[1] : nullptr);
+    CUDA_OK(cudaEventRecord(c->xdone[0], c->xstream));
+  }
+  for (int64_t k = 0; k < nb; k++) {
+    const int nt = (int)nt_of(k);
+    const BatchPlan &pl = plans[k % 3];
+    // ---- records of the batch -> device (ring of REC_RING pinned slots)
+    const int slot = (int)(c->rec_uses % REC_RING);
+    if (c->rec_uses >= REC_RING) CUDA_OK(cudaEventSynchronize(c->rec_ev[slot]));
+    c->rec_uses++;
+    TupleRec *hr = c->h_recs + (size_t)slot * c->batch, *dr = c->d_recs + (size_t)slot * c->batch;
+    std::memcpy(hr, pl.recs.data(), sizeof(TupleRec) * nt);
+    if (sh) CUDA_OK(cudaStreamWaitEvent(c->stream, c->xdone[k & 3], 0));
+    CUDA_OK(cudaMemcpyAsync(dr, hr, sizeof(TupleRec) * nt, cudaMemcpyHostToDevice, c->stream));
+    // per-kernel events around the first batches only: contraction [2,3], reduction [3,4]
     const bool sample = sampled < 4;
     if (sample) CUDA_OK(cudaEventRecord(c->ev[2], c->stream));
-    launch_contract(c, tp, nt, false);
+    launch_contract(c, dr, nt, false);
     n_contract++;
     if (sample) CUDA_OK(cudaEventRecord(c->ev[3], c->stream));
-    launch_reduce(c, tp, nt, false, c->d_total);
+    launch_reduce(c, dr, nt, false, c->d_total);
     n_reduce += 2;
     if (sample) CUDA_OK(cudaEventRecord(c->ev[4], c->stream));
     if (ct) {
-      launch_contract(c, tp, nt, true);
-      launch_reduce(c, tp, nt, true, c->d_total + 1);
+      launch_contract(c, dr, nt, true);
+      launch_reduce(c, dr, nt, true, c->d_total + 1);
       n_contract++;
       n_reduce += 2;
+    }
+    CUDA_OK(cudaEventRecord(c->rec_ev[slot], c->stream));
+    if (sh) CUDA_OK(cudaEventRecord(c->cdone[k & 3], c->stream));
+    // ---- next batch: host plan (and, sharded, its exchange on the side stream)
+    if (k + 1 < nb) {
+      if (!sh) make_plan(k + 1);
+      else {
+        CUDA_OK(cudaEventSynchronize(c->xdone[k & 3]));  // peers' requests for batch k+1 are on the host
+        if (k + 2 < nb) make_plan(k + 2);
+        if (k >= 1) CUDA_OK(cudaStreamWaitEvent(c->xstream, c->cdone[(k - 1) & 3], 0));  // region (k+1)%2 is free
+        exchange_step(c, k + 1, &plans[(k + 1) % 3], k + 2 < nb ? &plans[(k + 2) % 3] : nullptr);
+        CUDA_OK(cudaEventRecord(c->xdone[(k + 1) & 3], c->xstream));
+      }
     }
     if (sample) {
       CUDA_OK(cudaEventSynchronize(c->ev[4]));
@@ -599,69 +806,83 @@ void run_impl(atrip_b200_ctx *c, int64_t first, int64_t count, double *energy, d
       sampled++;
     }
   }
-  CUDA_OK(cudaEventRecord(e_end, c->stream));
+  CUDA_OK(cudaEventRecord(c->ev[1], c->stream));
   double tot[2];
   CUDA_OK(cudaMemcpyAsync(tot, c->d_total, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   CUDA_OK(cudaStreamSynchronize(c->stream));
+  if (sh) CUDA_OK(cudaStreamSynchronize(c->xstream));
   float ms = 0;
-  CUDA_OK(cudaEventElapsedTime(&ms, e_begin, e_end));
+  CUDA_OK(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]));
   int64_t real = 0;
-  for (int64_t t = first; t < first + count; t++)
-    real += !(c->tuples[t][0] == 0 && c->tuples[t][1] == 0 && c->tuples[t][2] == 0);
+  for (int64_t t = 0; t < count; t++) real += !is_fake(list[t]);
   c->timing[0] = ms;
   c->timing[1] = sampled ? ms_contract / sampled : 0;  // mean ms per sampled contraction launch
   c->timing[2] = sampled ? ms_reduce / sampled : 0;    // mean ms per sampled reduction (+sum) pair
   c->timing[3] = n_contract;
   c->timing[4] = n_reduce;
   c->timing[5] = (double)real;
+  c->timing[6] = c->exch_bytes;
+  c->timing[7] = c->exch_msgs;
   if (energy) *energy = tot[0];
   if (ct_energy) *ct_energy = ct ? tot[1] : tot[0];  // without J the reference's ct_energy == energy
 }
 
+void run_impl(atrip_b200_ctx *c, int64_t first, int64_t count, double *energy, double *ct_energy) {
+  REQUIRE(first >= 0 && count >= 0 && (size_t)(first + count) <= c->tuples.size(), "tuple range out of bounds");
+  run_list(c, c->tuples.data() + first, count, energy, ct_energy);
+}
+
+void set_tuples_impl(atrip_b200_ctx *c) {
+  int64_t need[3] = {0, 0, 0};
+  if (sharded(c)) cache_need(c->map, c->tuples.data(), c->tuples.size(), (size_t)c->batch, need);
+  ensure_caches(c, need);
+}
+
 void tuple_debug_impl(atrip_b200_ctx *c, int64_t a, int64_t b, int64_t cc, double *Tijk, double *Zijk, double *energy) {
   REQUIRE(a >= 0 && a <= b && b <= cc && cc < c->Nv && !(a == b && b == cc), "not a valid tuple a<=b<=c");
-  const int4 h = make_int4((int)a, (int)b, (int)cc, 0);
-  CUDA_OK(cudaMemcpyAsync(c->dbg_tuple, &h, sizeof(h), cudaMemcpyHostToDevice, c->stream));
-  CUDA_OK(cudaMemsetAsync(c->d_total, 0, 2 * sizeof(double), c->stream));
-  launch_contract(c, c->dbg_tuple, 1, false);
-  launch_reduce(c, c->dbg_tuple, 1, false, c->d_total);
+  const Tuple one{(uint64_t)a, (uint64_t)b, (uint64_t)cc};
+  double e = 0;
+  const uint64_t slot = c->rec_uses % REC_RING;  // the ring slot run_list is about to use
+  run_list(c, &one, 1, &e, nullptr);
   const size_t cube = (size_t)c->No * c->No * c->No;
   double *dT = nullptr, *dZ = nullptr;
   if (Tijk) dT = dalloc<double>(cube);
   if (Zijk) dZ = dalloc<double>(cube);
   if (Tijk || Zijk) {
-    ReduceParams P = reduce_params(c, c->dbg_tuple, 1, false);
+    ReduceParams P = reduce_params(c, c->d_recs + slot * c->batch, 1, false);
     cubes_kernel<<<grid_for(cube, c->nsm), 256, 0, c->stream>>>(P, 0, dT, dZ);
     CUDA_OK(cudaGetLastError());
   }
-  double tot[2];
-  CUDA_OK(cudaMemcpyAsync(tot, c->d_total, sizeof(tot), cudaMemcpyDeviceToHost, c->stream));
   if (Tijk) CUDA_OK(cudaMemcpyAsync(Tijk, dT, cube * 8, cudaMemcpyDeviceToHost, c->stream));
   if (Zijk) CUDA_OK(cudaMemcpyAsync(Zijk, dZ, cube * 8, cudaMemcpyDeviceToHost, c->stream));
   CUDA_OK(cudaStreamSynchronize(c->stream));
   if (dT) cudaFree(dT);
   if (dZ) cudaFree(dZ);
-  if (energy) *energy = tot[0];
+  if (energy) *energy = e;
 }
 
 void read_slice_impl(atrip_b200_ctx *c, int kind, int64_t x, int64_t y, double *out) {
-  const size_t No = c->No, Nv = c->Nv, Kp = c->Kp;
+  const size_t No = c->No, Nv = c->Nv;
+  const ShardMap &m = c->map;
   REQUIRE(x >= 0 && x < (int64_t)Nv, "slice index x out of range");
   size_t n = 0;
   const double *ax = nullptr, *by = nullptr, *vij = nullptr;
   if (kind == 100 || kind == 101 || kind == 201) {
     n = kind == 100 ? Nv * No * No : (kind == 101 ? No * No * No : No * No);
-    ax = c->AX + (size_t)x * No * No * Kp;
+    REQUIRE(m.ownerA(x) == m.me, "this rank does not own that slice");
+    ax = c->AX + (size_t)m.slotA(x) * slice_elems(c, KA);
   } else if (kind == 200) {
     REQUIRE(y >= 0 && y < (int64_t)Nv, "slice index y out of range");
     n = Nv * No;
-    by = c->BY + ((size_t)x + (size_t)y * Nv) * No * Kp;
+    const int64_t id = m.idB(x, y, false);
+    REQUIRE(m.ownerB(id) == m.me, "this rank does not own that slice");
+    by = c->BY + (size_t)m.slotB(id) * slice_elems(c, KB);
   } else if (kind == 202) {
     REQUIRE(y >= x && y < (int64_t)Nv, "VABIJ slices are stored for x <= y");
     n = No * No;
-    std::vector<int> one(1);
-    CUDA_OK(cudaMemcpy(one.data(), c->vtab + x + y * Nv, sizeof(int), cudaMemcpyDeviceToHost));
-    vij = c->VIJ + (size_t)one[0] * No * No;
+    const int64_t s = m.localV(x, y);
+    REQUIRE(s >= 0, "this rank does not own that slice");
+    vij = c->VIJ + (size_t)s * No * No;
   } else {
     throw Fail{"unknown slice kind"};
   }
@@ -672,6 +893,26 @@ void read_slice_impl(atrip_b200_ctx *c, int kind, int64_t x, int64_t y, double *
   CUDA_OK(cudaMemcpyAsync(out, d, n * 8, cudaMemcpyDeviceToHost, c->stream));
   CUDA_OK(cudaStreamSynchronize(c->stream));
   cudaFree(d);
+}
+
+void comm_init_impl(atrip_b200_ctx *c, const void *id128) {
+  NcclApi &N = nccl();
+  REQUIRE(N.ok, "NCCL is not available: " + N.error);
+  REQUIRE(!c->comm, "communicator already initialised");
+  ncclUniqueId id;
+  static_assert(sizeof(id) == 128, "ncclUniqueId is 128 bytes");
+  std::memcpy(&id, id128, sizeof(id));
+  NCCL_OK(N.CommInitRank(&c->comm, c->cfg.nranks, id, c->cfg.rank));
+}
+
+void allreduce_impl(atrip_b200_ctx *c, double *vals, int n) {
+  REQUIRE(n >= 0 && n <= 16, "at most 16 values");
+  if (c->cfg.nranks == 1 || n == 0) return;
+  REQUIRE(c->comm, "atrip_b200_allreduce needs atrip_b200_comm_init");
+  CUDA_OK(cudaMemcpyAsync(c->d_reduce, vals, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  NCCL_OK(nccl().AllReduce(c->d_reduce, c->d_reduce, (size_t)n, ncclFloat64, ncclSum, c->comm, c->stream));
+  CUDA_OK(cudaMemcpyAsync(vals, c->d_reduce, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(cudaStreamSynchronize(c->stream));
 }
 
 // register-resident DMMA loop: the FP64 tensor ceiling (same loop as tools/fp64_peak.cu)
@@ -791,7 +1032,7 @@ int atrip_b200_build_tuples(atrip_b200_ctx *c, int32_t distribution) {
     REQUIRE(distribution == 0 || distribution == 1, "distribution must be 0 (NAIVE) or 1 (GROUP_AND_SORT)");
     c->tuples = distribution == 0 ? naive_tuples(c->Nv, c->cfg.rank, c->cfg.nranks)
                                   : group_and_sort_tuples(c->Nv, c->cfg.rank, c->cfg.nranks, true);
-    upload_tuples(c);
+    set_tuples_impl(c);
   });
 }
 int atrip_b200_set_tuples(atrip_b200_ctx *c, const uint64_t *abc, int64_t n) {
@@ -804,7 +1045,7 @@ int atrip_b200_set_tuples(atrip_b200_ctx *c, const uint64_t *abc, int64_t n) {
               "tuple " + std::to_string(i) + " is not a<=b<=c<Nv (or the fake tuple)");
       c->tuples[i] = Tuple{a, b, cc};
     }
-    upload_tuples(c);
+    set_tuples_impl(c);
   });
 }
 int64_t atrip_b200_num_tuples(const atrip_b200_ctx *c) { return c ? (int64_t)c->tuples.size() : 0; }
@@ -827,6 +1068,27 @@ int atrip_b200_read_slice(atrip_b200_ctx *c, int32_t kind, int64_t x, int64_t y,
 int atrip_b200_last_timing(const atrip_b200_ctx *c, double *out6) {
   for (int i = 0; i < 6; i++) out6[i] = c->timing[i];
   return 0;
+}
+int atrip_b200_last_exchange(const atrip_b200_ctx *c, double *out2) {
+  out2[0] = c->timing[6];
+  out2[1] = c->timing[7];
+  return 0;
+}
+
+int atrip_b200_comm_unique_id(void *id128) {
+  return guarded(nullptr, [&] {
+    NcclApi &N = nccl();
+    REQUIRE(N.ok, "NCCL is not available: " + N.error);
+    ncclUniqueId id;
+    NCCL_OK(N.GetUniqueId(&id));
+    std::memcpy(id128, &id, sizeof(id));
+  });
+}
+int atrip_b200_comm_init(atrip_b200_ctx *c, const void *id128) {
+  return guarded(c, [&] { comm_init_impl(c, id128); });
+}
+int atrip_b200_allreduce(atrip_b200_ctx *c, double *vals, int32_t n) {
+  return guarded(c, [&] { allreduce_impl(c, vals, n); });
 }
 int64_t atrip_b200_kp(const atrip_b200_ctx *c) { return c->Kp; }
 int64_t atrip_b200_batch_tuples(const atrip_b200_ctx *c) { return c->batch; }
@@ -912,9 +1174,81 @@ int64_t atrip_b200_host_tuples(int32_t distribution, int64_t Nv, int32_t rank, i
   return n;
 }
 
+namespace {
+// reference slice kinds (Slice.hpp:99-108) -> store kind and id in that store
+bool kind_to_store(int32_t kind, int64_t x, int64_t y, int64_t Nv, const ShardMap &m, int *store, int64_t *id) {
+  if (x < 0 || x >= Nv) return false;
+  if (kind == 100 || kind == 101) { *store = KA; *id = x; return true; }
+  if (y < 0 || y >= Nv) return false;
+  if (kind == 200 || kind == 201) { *store = KB; *id = m.idB(x, y, false); return true; }
+  if (kind == 202 && x <= y) { *store = KV; *id = x + y * Nv; return true; }
+  return false;
+}
+}  // namespace
+
+int32_t atrip_b200_host_slice_slot(int32_t kind, int64_t x, int64_t y, int64_t Nv, int32_t nranks, int64_t *slot) {
+  if (nranks < 1 || Nv < 1) return -1;
+  const ShardMap m(Nv, nranks, 0);
+  int store;
+  int64_t id;
+  if (!kind_to_store(kind, x, y, Nv, m, &store, &id)) return -1;
+  if (store == KA) { if (slot) *slot = m.slotA(id); return m.ownerA(id); }
+  if (store == KB) { if (slot) *slot = m.slotB(id); return m.ownerB(id); }
+  if (slot) *slot = m.slotV1(x, y);
+  return m.ownerV(id);
+}
+int64_t atrip_b200_host_local_slot(int32_t kind, int64_t x, int64_t y, int64_t Nv, int32_t rank, int32_t nranks) {
+  if (nranks < 1 || Nv < 1 || rank < 0 || rank >= nranks) return -1;
+  const ShardMap m(Nv, nranks, rank);
+  if (kind == 203) {
+    if (x < 0 || x >= Nv) return -1;
+    const int64_t id = m.idB(x, x, true);
+    return m.ownerB(id) == rank ? m.slotB(id) : -1;
+  }
+  int store;
+  int64_t id;
+  if (!kind_to_store(kind, x, y, Nv, m, &store, &id)) return -1;
+  if (store == KA) return m.ownerA(id) == rank ? m.slotA(id) : -1;
+  if (store == KB) return m.ownerB(id) == rank ? m.slotB(id) : -1;
+  return m.localV(x, y);
+}
 int32_t atrip_b200_host_slice_owner(int32_t kind, int64_t x, int64_t y, int64_t Nv, int32_t nranks) {
-  if (kind == 100 || kind == 101) return (int32_t)(x % nranks);
-  return (int32_t)((x + y * Nv) % nranks);
+  return atrip_b200_host_slice_slot(kind, x, y, Nv, nranks, nullptr);
+}
+int atrip_b200_host_shard_sizes(int64_t Nv, int32_t rank, int32_t nranks, int64_t *out3) {
+  if (nranks < 1 || Nv < 1 || rank < 0 || rank >= nranks) { g_error = "atrip_b200_host_shard_sizes: bad arguments"; return 1; }
+  const ShardMap m(Nv, nranks, rank);
+  for (int k = 0; k < 3; k++) out3[k] = m.owned(k, rank);
+  return 0;
+}
+int64_t atrip_b200_host_plan_batch(int64_t Nv, int32_t rank, int32_t nranks, const uint64_t *abc, int64_t n,
+                                   const int64_t *cache_base3, int32_t *recs, int64_t *ranges, int64_t cap) {
+  if (nranks < 1 || Nv < 1 || rank < 0 || rank >= nranks || n < 0) { g_error = "atrip_b200_host_plan_batch: bad arguments"; return -1; }
+  const ShardMap m(Nv, nranks, rank);
+  std::vector<Tuple> t((size_t)n);
+  for (int64_t i = 0; i < n; i++) t[i] = Tuple{abc[3 * i], abc[3 * i + 1], abc[3 * i + 2]};
+  BatchPlan pl;
+  plan_batch(m, t.data(), (size_t)n, cache_base3, pl);
+  if (recs) std::memcpy(recs, pl.recs.data(), sizeof(TupleRec) * (size_t)n);
+  int64_t k = 0;
+  for (int p = 0; p < nranks; p++)
+    for (const FetchRange &fr : pl.fetch[(size_t)p]) {
+      if (k < cap && ranges) {
+        const int64_t v[5] = {p, fr.kind, fr.src_slot, fr.count, fr.dst_slot};
+        std::memcpy(ranges + 5 * k, v, sizeof(v));
+      }
+      k++;
+    }
+  return k;
+}
+int atrip_b200_host_cache_need(int64_t Nv, int32_t rank, int32_t nranks, const uint64_t *abc, int64_t n,
+                               int64_t batch, int64_t *out3) {
+  if (nranks < 1 || Nv < 1 || rank < 0 || rank >= nranks || n < 0 || batch < 1) { g_error = "atrip_b200_host_cache_need: bad arguments"; return 1; }
+  const ShardMap m(Nv, nranks, rank);
+  std::vector<Tuple> t((size_t)n);
+  for (int64_t i = 0; i < n; i++) t[i] = Tuple{abc[3 * i], abc[3 * i + 1], abc[3 * i + 2]};
+  cache_need(m, t.data(), (size_t)n, (size_t)batch, out3);
+  return 0;
 }
 
 }  // extern "C"

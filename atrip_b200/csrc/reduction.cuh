@@ -14,6 +14,7 @@
 // fixed order, so results are run-to-run deterministic and there is no per-tuple DtoH.
 #pragma once
 #include "common.cuh"
+#include "schedule.hpp"
 
 namespace ab {
 
@@ -25,12 +26,13 @@ constexpr int REDUCE_THREADS = 256;
 struct ReduceParams {
   int No, Nv;
   int ntuples;
-  const int4 *tuples;
+  const TupleRec *recs;  // the batch: tuple + store slots (vij: Vabij blocks of (b,c) (a,c) (a,b))
   const double *R;    // class cubes giving Tijk           [ntuples][3][No^3]
   const double *RZ;   // class cubes giving the Tijk inside Zijk (== R except in the cT pass)
   const double *eps_i, *eps_a, *Tai;
-  const double *VIJ;  // Vabij pair blocks [slot][No^2]
-  const int *vtab;    // y + z Nv -> slot
+  const double *VIJ;  // owned Vabij pair blocks [slot][No^2]
+  const double *VIJc; // fetch cache, addressed by slot - ownedV
+  int ownedV;
   double *e_tuple;    // [ntuples * nsplit] partial energies
   int nsplit;         // CTAs per tuple: CTA (t, s) takes the orbits o with o % nsplit == s
 };
@@ -52,21 +54,22 @@ reduce_kernel(const ReduceParams P) {
   double *sRed = sTc + P.No;                     // [32]
 
   const int tup = blockIdx.x;
-  const int4 abc = P.tuples[tup];
+  const TupleRec rec = P.recs[tup];
   const int tid = threadIdx.x;
   const int split = blockIdx.y;
-  if (abc.x == 0 && abc.y == 0 && abc.z == 0) {  // FAKE_TUPLE contributes nothing (Atrip.cxx:629)
+  if (rec.fake) {  // FAKE_TUPLE contributes nothing (Atrip.cxx:629)
     if (tid == 0) P.e_tuple[(size_t)tup * P.nsplit + split] = 0.0;
     return;
   }
-  const int a = abc.x, b = abc.y, c = abc.z;
+  const int a = rec.a, b = rec.b, c = rec.c;
   const int No = P.No, Nv = P.Nv;
   const size_t NoNo = (size_t)No * No, cube = NoNo * No;
   const double *Ck = P.R + (size_t)tup * 3 * cube, *Cj = Ck + cube, *Ci = Cj + cube;
   const double *Zk = P.RZ + (size_t)tup * 3 * cube, *Zj = Zk + cube, *Zi = Zj + cube;
-  const double *Vmat[3] = {P.VIJ + (size_t)P.vtab[b + c * Nv] * NoNo,   // VBCij
-                           P.VIJ + (size_t)P.vtab[a + c * Nv] * NoNo,   // VACij
-                           P.VIJ + (size_t)P.vtab[a + b * Nv] * NoNo};  // VABij
+  const double *Vmat[3];  // VBCij, VACij, VABij
+#pragma unroll
+  for (int q = 0; q < 3; q++)
+    Vmat[q] = rec.vij[q] >= P.ownedV ? P.VIJc + (size_t)(rec.vij[q] - P.ownedV) * NoNo : P.VIJ + (size_t)rec.vij[q] * NoNo;
   for (int i = tid; i < No; i += blockDim.x) {
     sEps[i] = P.eps_i[i];
     sTa[i] = P.Tai[a + (size_t)i * Nv];
@@ -224,11 +227,13 @@ __global__ void __launch_bounds__(256) accumulate_kernel(const double *e_tuple, 
 __global__ void cubes_kernel(const ReduceParams P, int tup, double *Tijk, double *Zijk) {
   const int No = P.No, Nv = P.Nv;
   const size_t NoNo = (size_t)No * No, cube = NoNo * No;
-  const int4 abc = P.tuples[tup];
+  const TupleRec rec = P.recs[tup];
+  const int3 abc = make_int3(rec.a, rec.b, rec.c);
   const double *Ck = P.R + (size_t)tup * 3 * cube, *Cj = Ck + cube, *Ci = Cj + cube;
-  const double *Vbc = P.VIJ + (size_t)P.vtab[abc.y + abc.z * Nv] * NoNo;
-  const double *Vac = P.VIJ + (size_t)P.vtab[abc.x + abc.z * Nv] * NoNo;
-  const double *Vab = P.VIJ + (size_t)P.vtab[abc.x + abc.y * Nv] * NoNo;
+  const double *Vm[3];
+  for (int q = 0; q < 3; q++)
+    Vm[q] = rec.vij[q] >= P.ownedV ? P.VIJc + (size_t)(rec.vij[q] - P.ownedV) * NoNo : P.VIJ + (size_t)rec.vij[q] * NoNo;
+  const double *Vbc = Vm[0], *Vac = Vm[1], *Vab = Vm[2];
   for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < cube; e += (size_t)gridDim.x * blockDim.x) {
     const int i = (int)(e % No), j = (int)((e / No) % No), k = (int)(e / NoNo);
     const double w = (Ck[i + (size_t)j * No + (size_t)k * NoNo] + Cj[i + (size_t)k * No + (size_t)j * NoNo]) +

@@ -101,10 +101,20 @@ Atrip::Output Atrip::run<double>(Atrip::Input<double> const &in) {
   cfg.No = (int64_t)No;
   cfg.Nv = (int64_t)Nv;
   cfg.batch_tuples = 0;
-  cfg.resident = 1;
+  // several ranks: every GPU stores the slices it owns and fetches the rest from its peers over
+  // NCCL (the reference's SliceUnion sources + MPI fetches); ATRIP_B200_REPLICATE=1 keeps a full
+  // replica per GPU instead (small problems)
+  const char *rep = std::getenv("ATRIP_B200_REPLICATE");
+  cfg.resident = (Atrip::np == 1 || (rep && rep[0] == '1')) ? 1 : 0;
   EngineHandle eng;
   ok(atrip_b200_create(&eng.ctx, &cfg), "create");
   LOG(0, "Atrip") << "engine: " << atrip_b200_version() << " on device " << cfg.device << "\n";
+  if (Atrip::np > 1) {  // one NCCL communicator over the ranks of Atrip::init's MPI communicator
+    unsigned char id[128] = {0};
+    if (Atrip::rank == 0) ok(atrip_b200_comm_unique_id(id), "comm_unique_id");
+    MPI_Bcast(id, 128, MPI_BYTE, 0, Atrip::communicator);
+    ok(atrip_b200_comm_init(eng.ctx, id), "comm_init");
+  }
 
   {  // replicated tensors (Atrip.cxx:176-215); Tai is negated for the ijkabc algorithm (:183-187)
     Seconds t;

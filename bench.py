@@ -195,6 +195,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
     ap.add_argument("--tuples-per-step", type=int, default=0)
+    ap.add_argument("--replicate", action="store_true",
+                    help="N>1: every GPU holds a full replica of the stores (no slice exchange)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
@@ -234,15 +236,21 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    def sum_over_ranks(vals):
-        t = torch.tensor(vals, dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.SUM)  # replaces MPI_Reduce(SUM), Atrip.cxx:1094-1107
-        return [float(x) for x in t.tolist()]
-
     No, Nv, tps = cfg["No"], cfg["Nv"], cfg["tuples_per_step"]
     K, W = args.steps, args.warmup
-    eng = atrip_b200.Engine(No, Nv, device=local, rank=rank, nranks=world, resident=True)
+    # N > 1: every GPU stores the slices it owns (RankMap round robin) and fetches the rest of each
+    # batch from its peers with ncclSend/ncclRecv on a side stream, one batch ahead of the compute
+    sharded = world > 1 and not args.replicate
+    eng = atrip_b200.Engine(No, Nv, device=local, rank=rank, nranks=world, resident=not sharded)
+    if world > 1:  # the engine's own NCCL communicator; its 128-byte id travels over torch.distributed
+        box = [capi.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        eng.comm_init(box[0])
+
+    def sum_over_ranks(vals):
+        # final energy reduction (replaces MPI_Reduce(SUM), Atrip.cxx:1094-1107): ncclAllReduce
+        return [float(x) for x in eng.allreduce(vals)]
+
     eng.fill_synthetic(SEED, cfg["scale"])
     n_list = eng.build_tuples(capi.GROUP_AND_SORT)
     tps = min(tps, n_list // (K + W))
@@ -264,8 +272,12 @@ def main():
     barrier()
     t0 = time.perf_counter()
     dev_ms, launches, tuples_done, ck_ms, rk_ms, ck_n, energy = 0.0, 0, 0.0, 0.0, 0.0, 0, 0.0
+    xbytes = xmsgs = 0.0
     for i in range(W, W + K):
         tm, tot = step(i)
+        ex = eng.last_exchange()
+        xbytes += ex["bytes"]
+        xmsgs += ex["messages"]
         dev_ms += tm["total_ms"]
         launches += tm["contract_launches"] + tm["reduce_launches"]
         tuples_done += tot[2]
@@ -337,6 +349,8 @@ def main():
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": cfg["name"] + ": " + cfg["desc"], "No": No, "Nv": Nv, "tuples_per_step": tps,
                        "tuples_per_step_all_ranks": tps * world, "distribution": "group_and_sort (GPU == node)",
+                       "stores": ("sharded: owned slices + NCCL send/recv fetch cache, prefetched one batch ahead"
+                                  if sharded else "replica on every GPU" if world > 1 else "single GPU"),
                        "l2_policy": "inputs larger than L2: every step walks new tuples (GBs of new slices)",
                        "seed": SEED, "scale": cfg["scale"]},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches * world,
@@ -350,6 +364,8 @@ def main():
             "frac_of_fp64_tensor_peak": value / (peak * world) if peak else None,
             "extrapolated_full_wall_s": flops_per_tuple * total_tuples / (value * 1e12),
             "energy_partial": -energy,
+            "exchange": {"rank0_recv_bytes_per_step": xbytes / K, "rank0_messages_per_step": xmsgs / K,
+                         "rank0_recv_GBps": xbytes / (dev_ms * 1e-3) / 1e9 if dev_ms else None},
         }
         print(json.dumps(line), flush=True)
     eng.close()

@@ -33,7 +33,8 @@ typedef struct atrip_b200_config {
   int64_t No, Nv;       /* occupied / virtual orbitals (lens[0] of epsilon_i/_a, Atrip.cxx:72-73) */
   int64_t batch_tuples; /* tuples per device batch; 0 = choose from No */
   int32_t resident;     /* 1: this rank stores every slice (replica); 0: only the slices it owns
-                           by RankMap round-robin plus a fetch cache */
+                           (atrip_b200_host_slice_owner) plus a fetch cache filled over NCCL;
+                           needs atrip_b200_comm_init before the first run when nranks > 1 */
   int32_t reserved;
 } atrip_b200_config;
 
@@ -96,6 +97,21 @@ int atrip_b200_tuple_debug(atrip_b200_ctx *ctx, int64_t a, int64_t b, int64_t c,
  *      201 TABIJ(x,y) [No,No]; 202 VABIJ(x,y) [No,No]  (Slice.hpp:99-108 names) */
 int atrip_b200_read_slice(atrip_b200_ctx *ctx, int32_t kind, int64_t x, int64_t y, double *out);
 
+/* ---- communicator of the job (replaces Atrip::init(MPI_Comm), Atrip.cxx:54-63, and the MPI calls
+ *      on the hot path: MPI_Isend/Irecv of slices, SliceUnion.cxx:456-462, 491-503, and the final
+ *      MPI_Reduce, Atrip.cxx:1094-1107).  One NCCL communicator with one rank per GPU: rank 0
+ *      calls atrip_b200_comm_unique_id and ships the 128 bytes to the other ranks through
+ *      whatever the host has (MPI_Bcast in the C++ API, torch.distributed in bench.py), then every
+ *      rank calls atrip_b200_comm_init.  With sharded stores (resident = 0) atrip_b200_run and
+ *      atrip_b200_tuple_debug are COLLECTIVE: every rank calls them with the same count (lists
+ *      are padded to equal length with the fake tuple for exactly this reason). */
+int atrip_b200_comm_unique_id(void *id128);
+int atrip_b200_comm_init(atrip_b200_ctx *ctx, const void *id128);
+/*      in-place SUM over all ranks of n <= 16 doubles in host memory (ncclAllReduce) */
+int atrip_b200_allreduce(atrip_b200_ctx *ctx, double *vals, int32_t n);
+/*      slice traffic of the last run on this rank: out[0] = bytes received, out[1] = messages */
+int atrip_b200_last_exchange(const atrip_b200_ctx *ctx, double *out2);
+
 /* ---- timing of the last atrip_b200_run, measured with CUDA events on the engine's stream:
  *      out[0] = total ms, out[1] = contraction kernel ms, out[2] = reduction kernel ms,
  *      out[3] = number of contraction launches, out[4] = number of reduction launches,
@@ -131,8 +147,30 @@ int atrip_b200_host_plan(int64_t No, int64_t smem_limit_bytes, int64_t *out11);
 int64_t atrip_b200_host_tuples(int32_t distribution, int64_t Nv, int32_t rank, int32_t nranks, int32_t pad,
                                uint64_t *abc, int64_t cap);
 /*      owner rank of a slice (replaces RankMap<F>::find, RankMap.cxx:35-85, one rank per node):
- *      kind 100/101 -> x % nranks; pair kinds -> (x + y Nv) % nranks (RankMap.cxx:43-44) */
+ *      kind 100/101 -> x % nranks; pair kinds (x,y) -> x % nranks: a pair lives with its FIRST
+ *      index, which equals the reference's (x + y Nv) % nranks (RankMap.cxx:43-44) whenever
+ *      Nv % nranks == 0 and keeps the co-location for any Nv.  VABIJ(x<=y) is additionally
+ *      replicated on y % nranks.  *slot (may be NULL) receives the slot in the owner's store. */
 int32_t atrip_b200_host_slice_owner(int32_t kind, int64_t x, int64_t y, int64_t Nv, int32_t nranks);
+int32_t atrip_b200_host_slice_slot(int32_t kind, int64_t x, int64_t y, int64_t Nv, int32_t nranks, int64_t *slot);
+/*      slot of a slice in the store of `rank`, or -1 if that rank does not hold it; kind 203 =
+ *      the transposed-hole twin (x,x)' of the diagonal pair slice */
+int64_t atrip_b200_host_local_slot(int32_t kind, int64_t x, int64_t y, int64_t Nv, int32_t rank, int32_t nranks);
+/*      owned slots per store of `rank`: out[0] AX (TAPHH+HHHA), out[1] BY (ABPH+TABHH, ordered
+ *      pairs + transposed diagonal), out[2] VIJ (ABHH) */
+int atrip_b200_host_shard_sizes(int64_t Nv, int32_t rank, int32_t nranks, int64_t *out3);
+/*      fetch schedule of one device batch (replaces build_local_database, SliceUnion.cxx:36-171,
+ *      and the per-tuple database exchange, Atrip.cxx:414-459): for the n tuples abc of `rank`
+ *      writes recs (n x 16 int32: a b c fake, AX slots of a b c, BY slots of (b,c) (a,c) (c,b)'
+ *      (a,b) (c,a)' (b,a)', VIJ slots of (b,c) (a,c) (a,b); slots >= owned count address the cache,
+ *      cache_base3 = first slot of the batch's cache region per store) and up to cap fetch ranges
+ *      (5 x int64 each: peer, store 0/1/2, first slot at the owner, count, first cache slot
+ *      relative to the region).  Returns the number of ranges, < 0 on error. */
+int64_t atrip_b200_host_plan_batch(int64_t Nv, int32_t rank, int32_t nranks, const uint64_t *abc, int64_t n,
+                                   const int64_t *cache_base3, int32_t *recs, int64_t *ranges, int64_t cap);
+/*      cache slots per store that any window of `batch` consecutive tuples of the list needs */
+int atrip_b200_host_cache_need(int64_t Nv, int32_t rank, int32_t nranks, const uint64_t *abc, int64_t n,
+                               int64_t batch, int64_t *out3);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,107 @@
+"""GPU, >= 2 devices: the sharded engine (owned slices + NCCL fetch cache) against the reference
+vectors and the oracle.  One process per GPU, as in production; skipped on a single-GPU box
+(the same host logic runs over gloo in tests/test_multirank_gloo.py).  Run with
+`gpurun --gpus 2 -- python -m pytest tests/test_gpu_multi.py -m gpu`."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import fh
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+E_ABS, E_REL, CUBE_REL = 1e-10, 1e-12, 1e-13
+
+
+def _worker(rank, world, q_id, q_out, case):
+    sys.path.insert(0, ROOT)
+    import atrip_b200
+    from atrip_b200 import capi
+    No, Nv, seed, scale, with_J, batch, host_tensors, debug = case
+    eng = atrip_b200.Engine(No, Nv, device=rank, rank=rank, nranks=world, with_J=with_J, batch_tuples=batch,
+                            resident=False)
+    if rank == 0:
+        uid = capi.comm_unique_id()
+        for _ in range(world - 1):
+            q_id.put(uid)
+    else:
+        uid = q_id.get(timeout=120)
+    eng.comm_init(uid)
+    if host_tensors is None:
+        eng.fill_synthetic(seed, scale)
+    else:
+        eng.load_all(*host_tensors)
+    n = eng.build_tuples(capi.GROUP_AND_SORT)
+    # walk the list in three uneven collective calls (exercises the bootstrap of each call)
+    cuts = [0, n // 3, n // 3 + 1, n]
+    e = ct = 0.0
+    xb = 0.0
+    for lo, hi in zip(cuts[:-1], cuts[1:]):
+        a, b = eng.run(lo, hi - lo)
+        e, ct = e + a, ct + b
+        xb += eng.last_exchange()["bytes"]
+    tot = eng.allreduce([e, ct])
+    dbg = []
+    for abc in debug:  # collective: every rank evaluates the same tuple, fetching what it lacks
+        ge, T, Z = eng.tuple_debug(*abc)
+        dbg.append((ge, T, Z))
+    q_out.put((rank, float(tot[0]), float(tot[1]), xb, dbg if rank == world - 1 else None))
+    eng.close()
+
+
+def run_case(world, case):
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    ctx = mp.get_context("spawn")
+    q_id, q_out = ctx.Queue(), ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, q_id, q_out, case)) for r in range(world)]
+    for p in procs:
+        p.start()
+    try:
+        res = sorted((q_out.get(timeout=600) for _ in range(world)), key=lambda x: x[0])
+        for p in procs:
+            p.join(timeout=60)
+            assert p.exitcode == 0
+    finally:
+        for p in procs:
+            if p.is_alive():
+                p.kill()
+    return res
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_runs_match_reference_vectors(oracle, golden, world):
+    """whole-run energies of the reference (np=1) reproduced by `world` GPUs with sharded stores,
+    device fill, small batches so that many exchange steps happen"""
+    for r in [golden["runs"][i] for i in (1, 4, 5)]:
+        res = run_case(world, (r["No"], r["Nv"], r["seed"], r["scale"], r["with_J"], 37, None, []))
+        for rank, e, ct, xb, _ in res:
+            assert abs(-e - fh(r["energy"])) <= E_ABS and abs(-e - fh(r["energy"])) <= E_REL * abs(e), (r, rank, -e)
+            ref_ct = fh(r["ct_energy"])
+            assert abs(-ct - ref_ct) <= E_ABS and abs(-ct - ref_ct) <= 1e-11 * max(abs(ref_ct), abs(e))
+            assert xb > 0, "no slices travelled: the sharded path was not exercised"
+
+
+def test_sharded_ingest_and_tuple_debug_match_oracle(oracle):
+    """host tensors ingested shard by shard; collective tuple_debug (remote slices of all three
+    kinds) against the oracle's Tijk / Zijk / energy; default batch size"""
+    from oracle.oracle import EPS_A, EPS_I, TABIJ, TAI, VABCI, VABIJ, VIJKA
+    No, Nv, seed, scale = 9, 21, 777, 0.05
+    t = oracle.inputs(No, Nv, seed=seed, scale=scale)
+    host = (t[EPS_I], t[EPS_A], t[TAI], t[TABIJ], t[VABIJ], t[VIJKA], t[VABCI])
+    debug = [(0, 1, 2), (1, 3, 5), (2, 2, 7), (4, 9, 9), (0, 2, 4), (17, 19, 20)]
+    want, _ = oracle.run(No, Nv, t)
+    res = run_case(2, (No, Nv, seed, scale, False, 0, host, debug))
+    for rank, e, ct, xb, dbg in res:
+        assert abs(-e - want) <= E_ABS and abs(-e - want) <= E_REL * abs(want)
+        if dbg is None:
+            continue
+        for abc, (ge, T, Z) in zip(debug, dbg):
+            oe, _, oT, oZ = oracle.tuple_energy(No, Nv, t, abc, want_cubes=True)
+            assert abs(ge - oe) <= E_REL * abs(oe), abc
+            assert np.abs(T - oT).max() <= CUBE_REL * np.abs(oT).max(), abc
+            assert np.abs(Z - oZ).max() <= CUBE_REL * np.abs(oZ).max(), abc
