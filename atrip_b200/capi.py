@@ -28,6 +28,7 @@ SYMBOLS = [
 ]
 
 NAIVE, GROUP_AND_SORT = 0, 1
+TRANSPORT_DEFAULT, TRANSPORT_NCCL, TRANSPORT_P2P = 0, 1, 2
 TA, VIJKA, VABCI, TABIJ, VABIJ = 100, 101, 200, 201, 202
 VABCI_T = 203  # host-side name of the transposed-hole twin (x,x)' of a diagonal pair slice
 
@@ -39,7 +40,7 @@ class EngineError(RuntimeError):
 class Config(C.Structure):
     _fields_ = [("device", C.c_int32), ("rank", C.c_int32), ("nranks", C.c_int32), ("with_J", C.c_int32),
                 ("No", C.c_int64), ("Nv", C.c_int64), ("batch_tuples", C.c_int64),
-                ("resident", C.c_int32), ("reserved", C.c_int32)]
+                ("resident", C.c_int32), ("transport", C.c_int32)]
 
 
 def lib_path():
@@ -227,10 +228,11 @@ def _ptr(a):
 
 
 class Engine:
-    def __init__(self, No, Nv, device=0, rank=0, nranks=1, with_J=False, batch_tuples=0, resident=True):
+    def __init__(self, No, Nv, device=0, rank=0, nranks=1, with_J=False, batch_tuples=0, resident=True,
+                 transport=0):
         self.L = load_library()
         self.No, self.Nv = int(No), int(Nv)
-        cfg = Config(device, rank, nranks, int(with_J), No, Nv, batch_tuples, int(resident), 0)
+        cfg = Config(device, rank, nranks, int(with_J), No, Nv, batch_tuples, int(resident), int(transport))
         self.ctx = C.c_void_p()
         self._ck(self.L.atrip_b200_create(C.byref(self.ctx), C.byref(cfg)))
 

@@ -12,6 +12,7 @@
 //     C_j[i + k No, j] = A_a [(i,k),:] B_cb + A_c^T[(i,k),:] B_ab      (P2 + H6, P3 + H1)
 //     C_i[j + k No, i] = A_b [(j,k),:] B_ca + A_c^T[(j,k),:] B_ba      (P6 + H4, P4 + H2)
 //     Tijk[i,j,k]      = C_k[i,j,k] + C_j[i,k,j] + C_i[j,k,i]
+// (the epilogue stores each class cube at Tijk's own [i + j No + k No^2], so kernel 2 just adds)
 // with A^T[(u,v),:] = A[(v,u),:].  The "transposition" is only a second TMA tensor map over the
 // same HBM store with the two row strides exchanged -- the permutations live in the operand
 // index maps, there is no reorder pass and no scratch GEMM output that gets re-accumulated.
@@ -180,16 +181,20 @@ contract_kernel(const __grid_constant__ ContractMaps M, const ContractParams P) 
       if (++stage == P.nstages) { stage = 0; phase ^= 1; }
     }
 
-    // epilogue: C fragment (row g, cols 2t, 2t+1) -> tile row/col through the same permutation
+    // epilogue: C fragment (row g, cols 2t, 2t+1) -> tile row/col through the same permutation.
+    // Every class cube is stored in Tijk's index order [i + j No + k No^2], so kernel 2 adds the
+    // three cubes element by element:  class 0 (u,v,n) = (i,j,k), class 1 (i,k,j), class 2 (j,k,i)
     double *Rc = P.R + ((size_t)tup * 3 + cls) * cube;
     const int u0 = (mt % P.utiles) * P.tu, v0 = (mt / P.utiles) * P.tv;
-    const int NoNo = P.No * P.No;
+    const size_t NoNo = (size_t)P.No * P.No;
+    const size_t su = cls == 2 ? (size_t)P.No : 1, sv = cls == 0 ? (size_t)P.No : NoNo,
+                 sn = cls == 0 ? NoNo : (cls == 1 ? (size_t)P.No : 1);
     int ul = (warp * MI * 8 + perm) % P.tu, vl = (warp * MI * 8 + perm) / P.tu;
 #pragma unroll
     for (int i = 0; i < MI; i++) {
       const int rl = warp * MI * 8 + i * 8 + perm;
       const int u = u0 + ul, v = v0 + vl;
-      const int m = u + v * P.No;
+      const size_t m = u * su + v * sv;
       ul += 8;
       while (ul >= P.tu) { ul -= P.tu; vl++; }
       if (rl < tile_rows && u < P.No && v < P.No) {
@@ -199,7 +204,7 @@ contract_kernel(const __grid_constant__ ContractMaps M, const ContractParams P) 
           for (int e = 0; e < 2; e++) {
             const int cf = 2 * t + e;
             const int col = nt * NI * 8 + j * 8 + 2 * (cf & 3) + (cf >> 2);
-            if (col < P.No) Rc[(size_t)m + (size_t)col * NoNo] = acc[i][j][e];
+            if (col < P.No) Rc[m + (size_t)col * sn] = acc[i][j][e];
           }
         }
       }

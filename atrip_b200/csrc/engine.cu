@@ -201,6 +201,10 @@ struct atrip_b200_ctx {
   int32_t *d_req_send = nullptr, *d_req_recv = nullptr;
   cudaEvent_t xdone[4]{}, cdone[4]{};
   double *d_reduce = nullptr;                             // all-reduce scratch
+  int transport = 0;                                      // 1 NCCL send/recv, 2 P2P pulls (copy engines)
+  int comm_sms = 0;                                       // SMs the contraction leaves to NCCL kernels
+  std::vector<double *> peer[5];                          // P2P: peers' AX, BY, VIJ, AXJ, BYJ (IPC mapped)
+  bool stores_dirty = true;                               // filled/loaded since the last rank barrier
   double exch_bytes = 0, exch_msgs = 0;                   // of the last run (received)
 
   // staging for ingest
@@ -337,7 +341,9 @@ void launch_contract(atrip_b200_ctx *c, const TupleRec *d_recs, int ntuples, boo
   P.recs = d_recs;
   P.R = useJ ? c->RJ : c->R;
   const long long nitems = 3LL * P.mtiles * P.ntiles * ntuples;
-  const int grid = (int)std::min<long long>(c->nsm, nitems);
+  // NCCL transport: leave a few SMs to the send/recv kernels of the side stream, otherwise they
+  // only run in the gaps between two persistent contraction launches
+  const int grid = (int)std::min<long long>(c->nsm - c->comm_sms, nitems);
   if (grid <= 0) return;
   void *args[2] = {useJ ? (void *)&c->mapsJ : (void *)&c->maps, (void *)&P};
   CUDA_OK(cudaLaunchKernel(c->plan.k->fn, dim3(grid), dim3((c->plan.nw + 1) * 32), args, c->plan.smem, c->stream));
@@ -422,6 +428,12 @@ void create_impl(atrip_b200_ctx *c) {
 
   // ---- which slices live here: everything (replica) or the slices this rank owns
   const int sn = (cfg.resident || cfg.nranks == 1) ? 1 : cfg.nranks;
+  REQUIRE(cfg.transport >= 0 && cfg.transport <= 2, "transport must be 0 (default), 1 (NCCL) or 2 (P2P)");
+  c->transport = sn == 1 ? 0 : (cfg.transport == 0 ? 2 : cfg.transport);
+  if (c->transport == 1) {
+    const char *e = std::getenv("ATRIP_B200_COMM_SMS");
+    c->comm_sms = std::max(0, std::min(c->nsm / 4, e ? std::atoi(e) : 4));
+  }
   c->map = ShardMap(cfg.Nv, sn, sn == 1 ? 0 : cfg.rank);
   const ShardMap &m = c->map;
   for (int k = 0; k < 3; k++) c->owned[k] = m.owned(k, m.me);
@@ -503,13 +515,15 @@ void create_impl(atrip_b200_ctx *c) {
   CUDA_OK(cudaMallocHost(&c->h_recs, sizeof(TupleRec) * REC_RING * c->batch));
   c->d_recs = dalloc<TupleRec>((size_t)REC_RING * c->batch);
 
-  if (sharded(c)) {
+  if (sharded(c) && c->transport == 1) {
     c->req_cap = request_capacity_ints((size_t)c->batch);
     const size_t n = 2 * (size_t)cfg.nranks * c->req_cap;
     CUDA_OK(cudaMallocHost(&c->h_req_send, n * sizeof(int32_t)));
     CUDA_OK(cudaMallocHost(&c->h_req_recv, n * sizeof(int32_t)));
     c->d_req_send = dalloc<int32_t>(n);
     c->d_req_recv = dalloc<int32_t>(n);
+  }
+  if (sharded(c)) {
     const int64_t none[3] = {0, 0, 0};
     ensure_caches(c, none);
   }
@@ -522,6 +536,9 @@ void destroy_impl(atrip_b200_ctx *c) {
   cudaSetDevice(c->cfg.device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->xstream) cudaStreamSynchronize(c->xstream);
+  for (auto &v : c->peer)
+    for (size_t p = 0; p < v.size(); p++)
+      if (v[p] && (int)p != c->cfg.rank) cudaIpcCloseMemHandle(v[p]);
   if (c->comm && nccl().ok) nccl().CommDestroy(c->comm);
   void *ptrs[] = {c->AX, c->BY, c->VIJ, c->AXJ, c->BYJ, c->eps_i, c->eps_a, c->Tai, c->xtab, c->btab,
                   c->vtab, c->xlist, c->ylist, c->zlist, c->tflag, c->vy, c->vz, c->R, c->RJ,
@@ -570,6 +587,7 @@ void fill_impl(atrip_b200_ctx *c, uint64_t seed, double scale) {
   }
   CUDA_OK(cudaGetLastError());
   CUDA_OK(cudaStreamSynchronize(c->stream));
+  c->stores_dirty = true;
 }
 
 void load_Tabij_impl(atrip_b200_ctx *c, const double *T) {
@@ -720,6 +738,37 @@ void exchange_step(atrip_b200_ctx *c, int64_t k, const BatchPlan *mine, const Ba
                             (size_t)n * c->req_cap * sizeof(int32_t), cudaMemcpyDeviceToHost, c->xstream));
 }
 
+// all ranks have finished filling their stores before anybody pulls from a peer
+void rank_barrier(atrip_b200_ctx *c) {
+  if (c->cfg.nranks == 1) return;
+  REQUIRE(c->comm, "sharded stores need atrip_b200_comm_init before running tuples");
+  CUDA_OK(cudaMemsetAsync(c->d_reduce, 0, sizeof(double), c->stream));
+  NCCL_OK(nccl().AllReduce(c->d_reduce, c->d_reduce, 1, ncclFloat64, ncclSum, c->comm, c->stream));
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+}
+
+// P2P transport: pull the remote slices of one batch straight out of the owners' stores into
+// cache region `par` with the copy engines (NVLink / NVSwitch); nothing runs on an SM and the
+// owner is not involved.  Replaces SliceUnion::receive + send (SliceUnion.cxx:365-505).
+void pull_step(atrip_b200_ctx *c, const BatchPlan *mine, int par) {
+  const bool J = c->have_J;
+  for (int p = 0; p < c->cfg.nranks; p++) {
+    if (p == c->cfg.rank) continue;
+    for (const FetchRange &fr : mine->fetch[(size_t)p]) {
+      const size_t el = slice_elems(c, fr.kind);
+      const size_t dst = (size_t)(par * c->cap[fr.kind] + fr.dst_slot) * el, src = (size_t)fr.src_slot * el;
+      const size_t bytes = (size_t)fr.count * el * sizeof(double);
+      CUDA_OK(cudaMemcpyAsync(cache_of(c, fr.kind, false) + dst, c->peer[fr.kind][(size_t)p] + src, bytes,
+                              cudaMemcpyDeviceToDevice, c->xstream));
+      if (J && fr.kind != KV)
+        CUDA_OK(cudaMemcpyAsync(cache_of(c, fr.kind, true) + dst, c->peer[3 + fr.kind][(size_t)p] + src, bytes,
+                                cudaMemcpyDeviceToDevice, c->xstream));
+      c->exch_bytes += (double)bytes * ((J && fr.kind != KV) ? 2 : 1);
+      c->exch_msgs += 1;
+    }
+  }
+}
+
 // Runs the tuples list[0..count) in device batches.  Replaces the main loop, Atrip.cxx:686-1057.
 // Sharded stores: COLLECTIVE -- every rank calls with the same count; slices of batch k+1 travel
 // on the side stream while batch k computes (two cache regions).
@@ -727,6 +776,7 @@ void run_list(atrip_b200_ctx *c, const Tuple *list, int64_t count, double *energ
   const bool ct = c->have_J;
   const bool sh = sharded(c);
   REQUIRE(!sh || c->comm, "sharded stores need atrip_b200_comm_init before running tuples");
+  REQUIRE(!sh || c->transport != 2 || !c->peer[0].empty(), "peer stores are not mapped");
   const int64_t nb = (count + c->batch - 1) / c->batch;
   auto nt_of = [&](int64_t k) { return (size_t)std::min<int64_t>(c->batch, count - k * c->batch); };
   auto base_of = [&](int64_t k, int64_t base[3]) {
@@ -746,15 +796,24 @@ void run_list(atrip_b200_ctx *c, const Tuple *list, int64_t count, double *energ
   double ms_contract = 0, ms_reduce = 0;
   int n_contract = 0, n_reduce = 0, sampled = 0;
   CUDA_OK(cudaEventRecord(c->ev[0], c->stream));
+  const bool p2p = sh && c->transport == 2;
+  if (sh && c->stores_dirty) {
+    rank_barrier(c);
+    c->stores_dirty = false;
+  }
   if (nb > 0) make_plan(0);
   if (sh && nb > 0) {
     // last run's compute may still read the caches / request buffers: order the side stream after it
     CUDA_OK(cudaEventRecord(c->cdone[3], c->stream));
     CUDA_OK(cudaStreamWaitEvent(c->xstream, c->cdone[3], 0));
-    exchange_step(c, -1, nullptr, &plans[0]);
-    CUDA_OK(cudaStreamSynchronize(c->xstream));
-    if (nb > 1) make_plan(1);
-    exchange_step(c, 0, &plans[0], nb > 1 ? &plans[1] : nullptr);
+    if (p2p) {
+      pull_step(c, &plans[0], 0);
+    } else {
+      exchange_step(c, -1, nullptr, &plans[0]);
+      CUDA_OK(cudaStreamSynchronize(c->xstream));
+      if (nb > 1) make_plan(1);
+      exchange_step(c, 0, &plans[0], nb > 1 ? &plans[1] : nullptr);
+    }
     CUDA_OK(cudaEventRecord(c->xdone[0], c->xstream));
   }
   for (int64_t k = 0; k < nb; k++) {
@@ -788,7 +847,12 @@ void run_list(atrip_b200_ctx *c, const Tuple *list, int64_t count, double *energ
     // ---- next batch: host plan (and, sharded, its exchange on the side stream)
     if (k + 1 < nb) {
       if (!sh) make_plan(k + 1);
-      else {
+      else if (p2p) {  // fully asynchronous: the host never waits for a transfer
+        make_plan(k + 1);
+        if (k >= 1) CUDA_OK(cudaStreamWaitEvent(c->xstream, c->cdone[(k - 1) & 3], 0));  // region (k+1)%2 is free
+        pull_step(c, &plans[(k + 1) % 3], (int)((k + 1) & 1));
+        CUDA_OK(cudaEventRecord(c->xdone[(k + 1) & 3], c->xstream));
+      } else {
         CUDA_OK(cudaEventSynchronize(c->xdone[k & 3]));  // peers' requests for batch k+1 are on the host
         if (k + 2 < nb) make_plan(k + 2);
         if (k >= 1) CUDA_OK(cudaStreamWaitEvent(c->xstream, c->cdone[(k - 1) & 3], 0));  // region (k+1)%2 is free
@@ -903,6 +967,35 @@ void comm_init_impl(atrip_b200_ctx *c, const void *id128) {
   static_assert(sizeof(id) == 128, "ncclUniqueId is 128 bytes");
   std::memcpy(&id, id128, sizeof(id));
   NCCL_OK(N.CommInitRank(&c->comm, c->cfg.nranks, id, c->cfg.rank));
+  if (!sharded(c) || c->transport != 2) return;
+  // P2P transport: every rank publishes CUDA IPC handles of its stores (all-gather over the new
+  // communicator) and maps the peers' stores into its own address space
+  const int n = c->cfg.nranks, me = c->cfg.rank;
+  double *mine[5] = {c->AX, c->BY, c->VIJ, c->AXJ, c->BYJ};
+  const int nh = c->cfg.with_J ? 5 : 3;
+  std::vector<cudaIpcMemHandle_t> all((size_t)n * 5);
+  for (int k = 0; k < nh; k++) CUDA_OK(cudaIpcGetMemHandle(&all[(size_t)me * 5 + k], mine[k]));
+  const size_t per = 5 * sizeof(cudaIpcMemHandle_t);
+  unsigned char *d = dalloc<unsigned char>(per * n);
+  CUDA_OK(cudaMemcpyAsync(d + per * me, &all[(size_t)me * 5], per, cudaMemcpyHostToDevice, c->stream));
+  NCCL_OK(N.GroupStart());
+  for (int p = 0; p < n; p++) {
+    if (p == me) continue;
+    NCCL_OK(N.Send(d + per * me, per, ncclUint8, p, c->comm, c->stream));
+    NCCL_OK(N.Recv(d + per * p, per, ncclUint8, p, c->comm, c->stream));
+  }
+  NCCL_OK(N.GroupEnd());
+  CUDA_OK(cudaMemcpyAsync(all.data(), d, per * n, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  cudaFree(d);
+  for (int k = 0; k < 5; k++) c->peer[k].assign((size_t)n, nullptr);
+  for (int p = 0; p < n; p++)
+    for (int k = 0; k < nh; k++) {
+      if (p == me) { c->peer[k][(size_t)p] = mine[k]; continue; }
+      void *ptr = nullptr;
+      CUDA_OK(cudaIpcOpenMemHandle(&ptr, all[(size_t)p * 5 + k], cudaIpcMemLazyEnablePeerAccess));
+      c->peer[k][(size_t)p] = (double *)ptr;
+    }
 }
 
 void allreduce_impl(atrip_b200_ctx *c, double *vals, int n) {
@@ -1001,17 +1094,18 @@ int atrip_b200_set_epsilon(atrip_b200_ctx *c, const double *ei, const double *ea
 int atrip_b200_set_Tai(atrip_b200_ctx *c, const double *Tai) {
   return guarded(c, [&] { CUDA_OK(cudaMemcpy(c->Tai, Tai, sizeof(double) * c->No * c->Nv, cudaMemcpyHostToDevice)); });
 }
-int atrip_b200_load_Tabij(atrip_b200_ctx *c, const double *T) { return guarded(c, [&] { load_Tabij_impl(c, T); }); }
-int atrip_b200_load_Vabij(atrip_b200_ctx *c, const double *V) { return guarded(c, [&] { load_Vabij_impl(c, V); }); }
+int atrip_b200_load_Tabij(atrip_b200_ctx *c, const double *T) { return guarded(c, [&] { c->stores_dirty = true; load_Tabij_impl(c, T); }); }
+int atrip_b200_load_Vabij(atrip_b200_ctx *c, const double *V) { return guarded(c, [&] { c->stores_dirty = true; load_Vabij_impl(c, V); }); }
 int atrip_b200_load_Vijka(atrip_b200_ctx *c, const double *V) {
-  return guarded(c, [&] { load_hhhp_impl(c, V, c->AX); });
+  return guarded(c, [&] { c->stores_dirty = true; load_hhhp_impl(c, V, c->AX); });
 }
 int atrip_b200_load_Vabci(atrip_b200_ctx *c, const double *V) {
-  return guarded(c, [&] { load_ppph_impl(c, V, c->BY); });
+  return guarded(c, [&] { c->stores_dirty = true; load_ppph_impl(c, V, c->BY); });
 }
 int atrip_b200_load_Jijka(atrip_b200_ctx *c, const double *V) {
   return guarded(c, [&] {
     REQUIRE(c->cfg.with_J, "context was created without with_J");
+    c->stores_dirty = true;
     load_hhhp_impl(c, V, c->AXJ);
     c->have_J = true;
   });
@@ -1019,6 +1113,7 @@ int atrip_b200_load_Jijka(atrip_b200_ctx *c, const double *V) {
 int atrip_b200_load_Jabci(atrip_b200_ctx *c, const double *V) {
   return guarded(c, [&] {
     REQUIRE(c->cfg.with_J, "context was created without with_J");
+    c->stores_dirty = true;
     load_ppph_impl(c, V, c->BYJ);
     c->have_J = true;
   });

@@ -4,10 +4,12 @@
 // (Equations.cxx:387-426) and get_energy_distinct / get_energy_same (Equations.cxx:101-238),
 // which the reference's GPU path runs as <<<1,1>>> kernels plus a cuMemAlloc and a blocking
 // 8-byte DtoH per tuple (Atrip.cxx:630-676).  Neither Tijk nor Zijk is materialised: one CTA
-// per tuple walks the orbits {I >= J >= K} of 8x8x8 tiles of the occupied cube, rebuilds
-//     Tijk[x,y,z] = C_k[x,y,z] + C_j[x,z,y] + C_i[y,z,x]
-// for the six permuted tiles of the orbit in shared memory (coalesced 64-byte segments from the
-// three class cubes of kernel 1), forms Zijk on the fly from Tai rows and the three Vabij
+// per (tuple, orbit split) walks the orbits {I >= J >= K} of 8x8x8 tiles of the occupied cube,
+// rebuilds
+//     Tijk[x,y,z] = C_k[x,y,z] + C_j[x,y,z] + C_i[x,y,z]
+// (kernel 1 stores its three class cubes in Tijk's own index order) for the six permuted tiles of
+// the orbit in shared memory -- every global load of an orbit is issued before the first use, so
+// a thread keeps up to 36 loads in flight --, forms Zijk on the fly from Tai rows and the three Vabij
 // blocks, evaluates the reference's triangular sum k <= j <= i with its weights literally
 // (needed for the a==b / b==c tuples on unsymmetric data), and reduces
 // with warp shuffles to one double per tuple.  The batch sum is a second, single-CTA kernel in a
@@ -43,7 +45,7 @@ __host__ __device__ inline size_t reduce_smem_bytes(int No, bool ct) {
 
 
 template <bool CT>
-__global__ void __launch_bounds__(REDUCE_THREADS, 3)
+__global__ void __launch_bounds__(REDUCE_THREADS, 2)
 reduce_kernel(const ReduceParams P) {
   extern __shared__ double sm[];
   double *Wt = sm;                               // [6][RTILE]
@@ -64,6 +66,7 @@ reduce_kernel(const ReduceParams P) {
   const int a = rec.a, b = rec.b, c = rec.c;
   const int No = P.No, Nv = P.Nv;
   const size_t NoNo = (size_t)No * No, cube = NoNo * No;
+  // the three class cubes of kernel 1, all indexed [i + j No + k No^2]
   const double *Ck = P.R + (size_t)tup * 3 * cube, *Cj = Ck + cube, *Ci = Cj + cube;
   const double *Zk = P.RZ + (size_t)tup * 3 * cube, *Zj = Zk + cube, *Zi = Zj + cube;
   const double *Vmat[3];  // VBCij, VACij, VABij
@@ -79,6 +82,9 @@ reduce_kernel(const ReduceParams P) {
   const double epsabc = P.eps_a[a] + P.eps_a[b] + P.eps_a[c];  // Atrip.cxx:643-646
   const bool same = (a == b) != (b == c);                     // Atrip.cxx:640-650
 
+  // block coordinates of permuted tile p = (blk[PX], blk[PY], blk[PZ]):
+  // 0 (I,J,K) 1 (I,K,J) 2 (J,I,K) 3 (J,K,I) 4 (K,I,J) 5 (K,J,I)
+  constexpr int PX[6] = {0, 0, 1, 1, 2, 2}, PY[6] = {1, 2, 0, 2, 0, 1}, PZ[6] = {2, 1, 2, 0, 1, 0};
   const int nb = (No + RT - 1) / RT;
   double esum = 0.0;
   const int l0 = tid & 7, l1 = (tid >> 3) & 7, l2 = tid >> 6;  // l2 in 0..3
@@ -96,58 +102,57 @@ reduce_kernel(const ReduceParams P) {
         const int c1 = eJK ? 0 : 1, c2 = eIJ ? 0 : 2, c3 = (eIJ && eJK) ? 0 : (eIJ ? 1 : 3),
                   c4 = (eIJ && eJK) ? 0 : (eJK ? 2 : 4), c5 = (eIJ && eJK) ? 0 : (eIJ ? 4 : (eJK ? 3 : 5));
         const int canon[6] = {0, c1, c2, c3, c4, c5};
-        __syncthreads();  // previous orbit fully consumed
-        // ---- pass 1: tiles <- C_k[x,y,z] + C_j[x,z,y]   (lanes run along x)
+        // ---- issue every global load of the orbit before touching shared memory: up to
+        //      6 tiles x 2 points x 3 class cubes per thread in flight (predicated, no branches)
+        double lk[6][2], lj[6][2], li[6][2];
 #pragma unroll
-        for (int X = 0; X < 3; X++)
+        for (int p = 0; p < 6; p++) {
+          const int x = blk[PX[p]] * RT + l0, y = blk[PY[p]] * RT + l1;
 #pragma unroll
-          for (int Y = 0; Y < 3; Y++) {
-            if (Y == X) continue;
-            const int Z = 3 - X - Y;
-            const int pi = X * 2 + ((Y > Z) ? 1 : 0);
-            if (canon[pi] != pi) continue;
-            const int x = blk[X] * RT + l0, y = blk[Y] * RT + l1;
-#pragma unroll
-            for (int it = 0; it < 2; it++) {
-              const int zl = l2 + 4 * it, z = blk[Z] * RT + zl;
-              double w = 0.0, wz = 0.0;
-              if (x < No && y < No && z < No) {
-                const size_t i1 = x + (size_t)y * No + (size_t)z * NoNo, i2 = x + (size_t)z * No + (size_t)y * NoNo;
-                w = Ck[i1] + Cj[i2];
-                if (CT) wz = Zk[i1] + Zj[i2];
-              }
-              Wt[pi * RTILE + l0 + RS1 * l1 + RS2 * zl] = w;
-              if (CT) Zt[pi * RTILE + l0 + RS1 * l1 + RS2 * zl] = wz;
-            }
+          for (int it = 0; it < 2; it++) {
+            const int z = blk[PZ[p]] * RT + l2 + 4 * it;
+            const bool ok = canon[p] == p && x < No && y < No && z < No;
+            const size_t idx = ok ? x + (size_t)y * No + (size_t)z * NoNo : 0;
+            lk[p][it] = ok ? Ck[idx] : 0.0;
+            lj[p][it] = ok ? Cj[idx] : 0.0;
+            li[p][it] = ok ? Ci[idx] : 0.0;
           }
-        // ---- Vabij blocks: Vb[mat][pair(X,Y)][xl + 8 yl] = Vmat[x + y No]
-        for (int e = tid; e < 18 * 64; e += REDUCE_THREADS) {
+        }
+        // Vabij blocks: Vb[mat][pair(X,Y)][xl + 8 yl] = Vmat[x + y No]
+        double lv[5];
+#pragma unroll
+        for (int q = 0; q < 5; q++) {
+          const int e = tid + REDUCE_THREADS * q;
           const int mat = e / 384, r = e - mat * 384, pr = r >> 6, xl = r & 7, yl = (r >> 3) & 7;
           const int X = pr >> 1, Y = (pr & 1) ? (X == 2 ? 1 : 2) : (X == 0 ? 1 : 0);
           const int x = blk[X] * RT + xl, y = blk[Y] * RT + yl;
-          Vb[e] = (x < No && y < No) ? Vmat[mat][x + (size_t)y * No] : 0.0;
+          lv[q] = (e < 18 * 64 && x < No && y < No) ? Vmat[mat < 3 ? mat : 0][x + (size_t)y * No] : 0.0;
         }
-        __syncthreads();
-        // ---- pass 2: tiles += C_i[y,z,x]   (lanes run along y)
+        __syncthreads();  // previous orbit fully consumed
 #pragma unroll
-        for (int X = 0; X < 3; X++)
+        for (int p = 0; p < 6; p++)
+          if (canon[p] == p) {
 #pragma unroll
-          for (int Y = 0; Y < 3; Y++) {
-            if (Y == X) continue;
-            const int Z = 3 - X - Y;
-            const int pi = X * 2 + ((Y > Z) ? 1 : 0);
-            if (canon[pi] != pi) continue;
-            const int y = blk[Y] * RT + l0, z = blk[Z] * RT + l1;
+            for (int it = 0; it < 2; it++)
+              Wt[p * RTILE + l0 + RS1 * l1 + RS2 * (l2 + 4 * it)] = (lk[p][it] + lj[p][it]) + li[p][it];
+          }
+#pragma unroll
+        for (int q = 0; q < 5; q++)
+          if (tid + REDUCE_THREADS * q < 18 * 64) Vb[tid + REDUCE_THREADS * q] = lv[q];
+        if (CT) {  // (cT): Zijk comes from the V-pass cubes, Tijk (above) from the J pass
+#pragma unroll
+          for (int p = 0; p < 6; p++) {
+            const int x = blk[PX[p]] * RT + l0, y = blk[PY[p]] * RT + l1;
 #pragma unroll
             for (int it = 0; it < 2; it++) {
-              const int xl = l2 + 4 * it, x = blk[X] * RT + xl;
-              if (x < No && y < No && z < No) {
-                const size_t i3 = y + (size_t)z * No + (size_t)x * NoNo;
-                Wt[pi * RTILE + xl + RS1 * l0 + RS2 * l1] += Ci[i3];
-                if (CT) Zt[pi * RTILE + xl + RS1 * l0 + RS2 * l1] += Zi[i3];
-              }
+              const int z = blk[PZ[p]] * RT + l2 + 4 * it;
+              const bool ok = canon[p] == p && x < No && y < No && z < No;
+              const size_t idx = ok ? x + (size_t)y * No + (size_t)z * NoNo : 0;
+              const double wz = ok ? (Zk[idx] + Zj[idx]) + Zi[idx] : 0.0;
+              if (canon[p] == p) Zt[p * RTILE + l0 + RS1 * l1 + RS2 * (l2 + 4 * it)] = wz;
             }
           }
+        }
         __syncthreads();
         // ---- energy of the (i in I, j in J, k in K) points with k <= j <= i
 #pragma unroll
@@ -236,8 +241,7 @@ __global__ void cubes_kernel(const ReduceParams P, int tup, double *Tijk, double
   const double *Vbc = Vm[0], *Vac = Vm[1], *Vab = Vm[2];
   for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < cube; e += (size_t)gridDim.x * blockDim.x) {
     const int i = (int)(e % No), j = (int)((e / No) % No), k = (int)(e / NoNo);
-    const double w = (Ck[i + (size_t)j * No + (size_t)k * NoNo] + Cj[i + (size_t)k * No + (size_t)j * NoNo]) +
-                     Ci[j + (size_t)k * No + (size_t)i * NoNo];
+    const double w = (Ck[e] + Cj[e]) + Ci[e];  // the class cubes share Tijk's index order
     if (Tijk) Tijk[e] = w;
     if (Zijk)
       Zijk[e] = ((w + P.Tai[abc.x + (size_t)i * Nv] * Vbc[j + (size_t)k * No]) +

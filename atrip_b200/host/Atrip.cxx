@@ -106,6 +106,8 @@ Atrip::Output Atrip::run<double>(Atrip::Input<double> const &in) {
   // replica per GPU instead (small problems)
   const char *rep = std::getenv("ATRIP_B200_REPLICATE");
   cfg.resident = (Atrip::np == 1 || (rep && rep[0] == '1')) ? 1 : 0;
+  const char *tr = std::getenv("ATRIP_B200_TRANSPORT");  // 1 = NCCL send/recv, 2 = P2P copy engines
+  cfg.transport = tr ? std::atoi(tr) : 0;
   EngineHandle eng;
   ok(atrip_b200_create(&eng.ctx, &cfg), "create");
   LOG(0, "Atrip") << "engine: " << atrip_b200_version() << " on device " << cfg.device << "\n";

@@ -197,6 +197,8 @@ def main():
     ap.add_argument("--tuples-per-step", type=int, default=0)
     ap.add_argument("--replicate", action="store_true",
                     help="N>1: every GPU holds a full replica of the stores (no slice exchange)")
+    ap.add_argument("--transport", type=int, default=0, choices=[0, 1, 2],
+                    help="N>1 slice exchange: 1 NCCL send/recv, 2 P2P copy-engine pulls, 0 engine default")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
@@ -241,7 +243,8 @@ def main():
     # N > 1: every GPU stores the slices it owns (RankMap round robin) and fetches the rest of each
     # batch from its peers with ncclSend/ncclRecv on a side stream, one batch ahead of the compute
     sharded = world > 1 and not args.replicate
-    eng = atrip_b200.Engine(No, Nv, device=local, rank=rank, nranks=world, resident=not sharded)
+    eng = atrip_b200.Engine(No, Nv, device=local, rank=rank, nranks=world, resident=not sharded,
+                            transport=args.transport)
     if world > 1:  # the engine's own NCCL communicator; its 128-byte id travels over torch.distributed
         box = [capi.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(box, src=0)
@@ -349,7 +352,9 @@ def main():
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": cfg["name"] + ": " + cfg["desc"], "No": No, "Nv": Nv, "tuples_per_step": tps,
                        "tuples_per_step_all_ranks": tps * world, "distribution": "group_and_sort (GPU == node)",
-                       "stores": ("sharded: owned slices + NCCL send/recv fetch cache, prefetched one batch ahead"
+                       "stores": ("sharded: owned slices + fetch cache prefetched one batch ahead on a side stream, "
+                                  + {0: "engine default transport", 1: "ncclSend/ncclRecv",
+                                     2: "P2P copy-engine pulls over NVLink"}[args.transport]
                                   if sharded else "replica on every GPU" if world > 1 else "single GPU"),
                        "l2_policy": "inputs larger than L2: every step walks new tuples (GBs of new slices)",
                        "seed": SEED, "scale": cfg["scale"]},

@@ -35,7 +35,12 @@ typedef struct atrip_b200_config {
   int32_t resident;     /* 1: this rank stores every slice (replica); 0: only the slices it owns
                            (atrip_b200_host_slice_owner) plus a fetch cache filled over NCCL;
                            needs atrip_b200_comm_init before the first run when nranks > 1 */
-  int32_t reserved;
+  int32_t transport;    /* how remote slices travel when resident = 0 (ignored otherwise):
+                           0 = default (currently 2), 1 = ncclSend/ncclRecv groups on a side stream,
+                           the owner pushes what the peers' request lists ask for; 2 = peer-to-peer
+                           pulls over NVLink by the copy engines (cudaMemcpyAsync from the owner's
+                           store, mapped through CUDA IPC): no SM is taken from the contraction and
+                           the owner does not take part */
 } atrip_b200_config;
 
 /* ---- lifecycle (replaces the ACC set-up in Atrip::run, Atrip.cxx:78-171, 217-218, 364-380) */
@@ -102,9 +107,11 @@ int atrip_b200_read_slice(atrip_b200_ctx *ctx, int32_t kind, int64_t x, int64_t 
  *      MPI_Reduce, Atrip.cxx:1094-1107).  One NCCL communicator with one rank per GPU: rank 0
  *      calls atrip_b200_comm_unique_id and ships the 128 bytes to the other ranks through
  *      whatever the host has (MPI_Bcast in the C++ API, torch.distributed in bench.py), then every
- *      rank calls atrip_b200_comm_init.  With sharded stores (resident = 0) atrip_b200_run and
- *      atrip_b200_tuple_debug are COLLECTIVE: every rank calls them with the same count (lists
- *      are padded to equal length with the fake tuple for exactly this reason). */
+ *      rank calls atrip_b200_comm_init (collective; with transport 2 it also maps the peers'
+ *      stores).  With sharded stores and transport 1 atrip_b200_run and atrip_b200_tuple_debug are
+ *      COLLECTIVE: every rank calls them with the same count (lists are padded to equal length
+ *      with the fake tuple for exactly this reason).  With transport 2 only the first run after
+ *      the stores were (re)filled synchronises the ranks. */
 int atrip_b200_comm_unique_id(void *id128);
 int atrip_b200_comm_init(atrip_b200_ctx *ctx, const void *id128);
 /*      in-place SUM over all ranks of n <= 16 doubles in host memory (ncclAllReduce) */

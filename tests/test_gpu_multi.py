@@ -1,5 +1,5 @@
-"""GPU, >= 2 devices: the sharded engine (owned slices + NCCL fetch cache) against the reference
-vectors and the oracle.  One process per GPU, as in production; skipped on a single-GPU box
+"""GPU, >= 2 devices: the sharded engine (owned slices + fetch cache, both transports: NCCL
+send/recv and P2P copy-engine pulls) against the reference vectors and the oracle.  One process per GPU, as in production; skipped on a single-GPU box
 (the same host logic runs over gloo in tests/test_multirank_gloo.py).  Run with
 `gpurun --gpus 2 -- python -m pytest tests/test_gpu_multi.py -m gpu`."""
 import os
@@ -19,9 +19,9 @@ def _worker(rank, world, q_id, q_out, case):
     sys.path.insert(0, ROOT)
     import atrip_b200
     from atrip_b200 import capi
-    No, Nv, seed, scale, with_J, batch, host_tensors, debug = case
+    No, Nv, seed, scale, with_J, batch, host_tensors, debug, transport = case
     eng = atrip_b200.Engine(No, Nv, device=rank, rank=rank, nranks=world, with_J=with_J, batch_tuples=batch,
-                            resident=False)
+                            resident=False, transport=transport)
     if rank == 0:
         uid = capi.comm_unique_id()
         for _ in range(world - 1):
@@ -73,12 +73,13 @@ def run_case(world, case):
     return res
 
 
+@pytest.mark.parametrize("transport", [1, 2], ids=["nccl", "p2p"])
 @pytest.mark.parametrize("world", [2, 4])
-def test_sharded_runs_match_reference_vectors(oracle, golden, world):
+def test_sharded_runs_match_reference_vectors(oracle, golden, world, transport):
     """whole-run energies of the reference (np=1) reproduced by `world` GPUs with sharded stores,
     device fill, small batches so that many exchange steps happen"""
     for r in [golden["runs"][i] for i in (1, 4, 5)]:
-        res = run_case(world, (r["No"], r["Nv"], r["seed"], r["scale"], r["with_J"], 37, None, []))
+        res = run_case(world, (r["No"], r["Nv"], r["seed"], r["scale"], r["with_J"], 37, None, [], transport))
         for rank, e, ct, xb, _ in res:
             assert abs(-e - fh(r["energy"])) <= E_ABS and abs(-e - fh(r["energy"])) <= E_REL * abs(e), (r, rank, -e)
             ref_ct = fh(r["ct_energy"])
@@ -86,7 +87,8 @@ def test_sharded_runs_match_reference_vectors(oracle, golden, world):
             assert xb > 0, "no slices travelled: the sharded path was not exercised"
 
 
-def test_sharded_ingest_and_tuple_debug_match_oracle(oracle):
+@pytest.mark.parametrize("transport", [1, 2], ids=["nccl", "p2p"])
+def test_sharded_ingest_and_tuple_debug_match_oracle(oracle, transport):
     """host tensors ingested shard by shard; collective tuple_debug (remote slices of all three
     kinds) against the oracle's Tijk / Zijk / energy; default batch size"""
     from oracle.oracle import EPS_A, EPS_I, TABIJ, TAI, VABCI, VABIJ, VIJKA
@@ -95,7 +97,7 @@ def test_sharded_ingest_and_tuple_debug_match_oracle(oracle):
     host = (t[EPS_I], t[EPS_A], t[TAI], t[TABIJ], t[VABIJ], t[VIJKA], t[VABCI])
     debug = [(0, 1, 2), (1, 3, 5), (2, 2, 7), (4, 9, 9), (0, 2, 4), (17, 19, 20)]
     want, _ = oracle.run(No, Nv, t)
-    res = run_case(2, (No, Nv, seed, scale, False, 0, host, debug))
+    res = run_case(2, (No, Nv, seed, scale, False, 0, host, debug, transport))
     for rank, e, ct, xb, dbg in res:
         assert abs(-e - want) <= E_ABS and abs(-e - want) <= E_REL * abs(want)
         if dbg is None:
