@@ -34,6 +34,18 @@ namespace ab {
 
 constexpr int MAX_STAGES = 12;
 
+// Storage of a class cube: 8x8x8 tiles, each 4 KB contiguous ([x + 8 y + 64 z] inside the tile),
+// tiles ordered [X + nb Y + nb^2 Z], nb = ceil(No/8).  Kernel 2 reads whole tiles (full 128-byte
+// lines; a plain [i + j No + k No^2] cube costs it 2x the DRAM traffic, ncu r01b).
+__host__ __device__ inline size_t cube_blocked_elems(int No) {
+  const size_t nb = (size_t)(No + 7) / 8;
+  return nb * nb * nb * 512;
+}
+__host__ __device__ inline size_t cube_offset(int No, int i, int j, int k) {
+  const size_t nb = (size_t)(No + 7) / 8;
+  return (((size_t)(k >> 3) * nb + (j >> 3)) * nb + (i >> 3)) * 512 + (i & 7) + 8 * (j & 7) + 64 * (k & 7);
+}
+
 // tensor maps of the owned stores and of the fetch caches (same layouts; a rank that stores
 // everything passes the owned maps twice)
 struct ContractMaps {
@@ -44,6 +56,7 @@ struct ContractMaps {
 struct ContractParams {
   int No, Nv, Kp;
   int nk;       // Kp / KC: K chunks per operand pair (a class runs 2*nk chunks)
+  int last_steps;  // k-steps (of 4) with data in the last chunk: ceil((No + Nv - (nk-1) KC) / 4)
   int tu, tv;   // row tile = tu values of u (fast) x tv values of v  ->  tu*tv rows (u + v No = row of C)
   int utiles;   // ceil(No / tu)
   int mtiles;   // utiles * ceil(No / tv)
@@ -54,7 +67,8 @@ struct ContractParams {
   int ntuples;
   int ownedA, ownedB;      // slots >= owned address the cache maps (schedule.hpp)
   const TupleRec *recs;    // the batch: tuple + store slots of its slices (built on the host)
-  double *R;               // [ntuples][3][No^3] class cubes C_k, C_j, C_i
+  double *R;               // [ntuples][3][cube_stride] class cubes C_k, C_j, C_i (8x8x8-blocked)
+  size_t cube_stride;      // doubles per stored cube = ceil(No/8)^3 * 512
 };
 
 __host__ __device__ inline size_t contract_stage_bytes(int arows, int NI) {
@@ -94,7 +108,6 @@ contract_kernel(const __grid_constant__ ContractMaps M, const ContractParams P) 
 
   const long long per_tuple = 3LL * P.mtiles * P.ntiles;
   const long long nitems = per_tuple * P.ntuples;
-  const size_t cube = (size_t)P.No * P.No * P.No;
   int stage = 0;
   uint32_t phase = 0;
 
@@ -164,17 +177,25 @@ contract_kernel(const __grid_constant__ ContractMaps M, const ContractParams P) 
     for (int ch = 0; ch < nchunks; ch++) {
       mbar_wait(&full_bar[stage], phase);
       const unsigned char *sb = base + (size_t)stage * stage_bytes;
-#pragma unroll
-      for (int s = 0; s < 4; s++) {
+      // one k-step = 4 values of kappa: MI + NI fragment loads feed MI x NI DMMA.8x8x4
+      auto kstep = [&](uint32_t col) {
         double af[MI], bf[NI];
 #pragma unroll
-        for (int i = 0; i < MI; i++) af[i] = *reinterpret_cast<const double *>(sb + offA + i * 1024 + cs[s]);
+        for (int i = 0; i < MI; i++) af[i] = *reinterpret_cast<const double *>(sb + offA + i * 1024 + col);
 #pragma unroll
-        for (int j = 0; j < NI; j++) bf[j] = *reinterpret_cast<const double *>(sb + offB + j * 1024 + cs[s]);
+        for (int j = 0; j < NI; j++) bf[j] = *reinterpret_cast<const double *>(sb + offB + j * 1024 + col);
 #pragma unroll
         for (int i = 0; i < MI; i++)
 #pragma unroll
           for (int j = 0; j < NI; j++) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+      };
+      if (ch != P.nk - 1 && ch != nchunks - 1) {
+#pragma unroll
+        for (int s = 0; s < 4; s++) kstep(cs[s]);
+      } else {
+        // last chunk of an operand pair: only the k-steps that hold data (the rest of the
+        // 16-wide chunk is the zero padding of Kp)
+        for (int s = 0; s < P.last_steps; s++) kstep((uint32_t)(((2 * s + (t >> 1)) ^ perm) * 16));
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty_bar[stage]);
@@ -182,19 +203,21 @@ contract_kernel(const __grid_constant__ ContractMaps M, const ContractParams P) 
     }
 
     // epilogue: C fragment (row g, cols 2t, 2t+1) -> tile row/col through the same permutation.
-    // Every class cube is stored in Tijk's index order [i + j No + k No^2], so kernel 2 adds the
-    // three cubes element by element:  class 0 (u,v,n) = (i,j,k), class 1 (i,k,j), class 2 (j,k,i)
-    double *Rc = P.R + ((size_t)tup * 3 + cls) * cube;
+    // Every class cube is stored at Tijk's own (i,j,k) -- class 0 (u,v,n) = (i,j,k), class 1
+    // (i,k,j), class 2 (j,k,i) -- in the 8x8x8-blocked layout kernel 2 streams (cube_offset):
+    // the offset is separable, off(i,j,k) = gi(i) + gj(j) + gk(k).
+    double *Rc = P.R + ((size_t)tup * 3 + cls) * P.cube_stride;
     const int u0 = (mt % P.utiles) * P.tu, v0 = (mt / P.utiles) * P.tv;
-    const size_t NoNo = (size_t)P.No * P.No;
-    const size_t su = cls == 2 ? (size_t)P.No : 1, sv = cls == 0 ? (size_t)P.No : NoNo,
-                 sn = cls == 0 ? NoNo : (cls == 1 ? (size_t)P.No : 1);
+    const int nb = (P.No + 7) >> 3;
+    auto gi = [&](int i) { return (size_t)(i >> 3) * 512 + (i & 7); };
+    auto gj = [&](int j) { return (size_t)(j >> 3) * nb * 512 + 8 * (j & 7); };
+    auto gk = [&](int k) { return (size_t)(k >> 3) * nb * nb * 512 + 64 * (k & 7); };
     int ul = (warp * MI * 8 + perm) % P.tu, vl = (warp * MI * 8 + perm) / P.tu;
 #pragma unroll
     for (int i = 0; i < MI; i++) {
       const int rl = warp * MI * 8 + i * 8 + perm;
       const int u = u0 + ul, v = v0 + vl;
-      const size_t m = u * su + v * sv;
+      const size_t m = cls == 0 ? gi(u) + gj(v) : (cls == 1 ? gi(u) + gk(v) : gj(u) + gk(v));
       ul += 8;
       while (ul >= P.tu) { ul -= P.tu; vl++; }
       if (rl < tile_rows && u < P.No && v < P.No) {
@@ -204,7 +227,7 @@ contract_kernel(const __grid_constant__ ContractMaps M, const ContractParams P) 
           for (int e = 0; e < 2; e++) {
             const int cf = 2 * t + e;
             const int col = nt * NI * 8 + j * 8 + 2 * (cf & 3) + (cf >> 2);
-            if (col < P.No) Rc[m + (size_t)col * sn] = acc[i][j][e];
+            if (col < P.No) Rc[m + (cls == 0 ? gk(col) : (cls == 1 ? gj(col) : gi(col)))] = acc[i][j][e];
           }
         }
       }

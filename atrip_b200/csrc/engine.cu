@@ -327,6 +327,7 @@ void launch_contract(atrip_b200_ctx *c, const TupleRec *d_recs, int ntuples, boo
   P.Nv = c->Nv;
   P.Kp = c->Kp;
   P.nk = c->Kp / KC;
+  P.last_steps = (c->No + c->Nv - (P.nk - 1) * KC + 3) / 4;
   P.tu = c->plan.tu;
   P.tv = c->plan.tv;
   P.utiles = c->plan.utiles;
@@ -340,6 +341,7 @@ void launch_contract(atrip_b200_ctx *c, const TupleRec *d_recs, int ntuples, boo
   P.ownedB = (int)c->owned[KB];
   P.recs = d_recs;
   P.R = useJ ? c->RJ : c->R;
+  P.cube_stride = cube_blocked_elems(c->No);
   const long long nitems = 3LL * P.mtiles * P.ntiles * ntuples;
   // NCCL transport: leave a few SMs to the send/recv kernels of the side stream, otherwise they
   // only run in the gaps between two persistent contraction launches
@@ -357,6 +359,7 @@ ReduceParams reduce_params(atrip_b200_ctx *c, const TupleRec *d_recs, int ntuple
   P.recs = d_recs;
   P.R = ct ? c->RJ : c->R;
   P.RZ = c->R;
+  P.cube_stride = cube_blocked_elems(c->No);
   P.eps_i = c->eps_i;
   P.eps_a = c->eps_a;
   P.Tai = c->Tai;
@@ -364,9 +367,20 @@ ReduceParams reduce_params(atrip_b200_ctx *c, const TupleRec *d_recs, int ntuple
   P.VIJc = c->cV ? c->cV : c->VIJ;
   P.ownedV = (int)c->owned[KV];
   P.e_tuple = c->e_tuple;
-  // enough CTAs to fill the GPU a few times over even when a batch has few tuples (large No)
+  // CTAs per tuple: fill the 2-CTA/SM slots in whole waves (a batch has few tuples when No is
+  // large), but keep several orbits per CTA so its prologue (eps, Tai rows) stays amortised
   const int nb = (c->No + RT - 1) / RT, orbits = nb * (nb + 1) * (nb + 2) / 6;
-  P.nsplit = std::max(1, std::min(std::min(orbits, 64), (c->nsm * 6 + ntuples - 1) / std::max(1, ntuples)));
+  const double slots = 2.0 * c->nsm;
+  int best = 1;
+  double best_score = -1;
+  for (int ns = 1; ns <= std::min(orbits, 64); ns++) {
+    const double waves = (double)ntuples * ns / slots;
+    const double fill = waves / std::ceil(waves);
+    const double per_cta = (double)orbits / ns;
+    const double score = fill * (per_cta / (per_cta + 1.0)) * (waves >= 2.5 ? 1.0 : 0.8 + 0.08 * waves);
+    if (score > best_score + 1e-9) { best_score = score; best = ns; }
+  }
+  P.nsplit = best;
   return P;
 }
 
@@ -497,7 +511,7 @@ void create_impl(atrip_b200_ctx *c) {
   c->Tai = dalloc<double>(No * Nv);
 
   // ---- work buffers: a batch keeps roughly 8 work items per SM in flight and <= 1 GiB of cubes
-  const size_t cube3 = 3 * No * No * No;
+  const size_t cube3 = 3 * cube_blocked_elems(c->No);
   long long batch = cfg.batch_tuples;
   if (batch <= 0) {
     const long long per_tuple = 3LL * c->plan.mtiles * c->plan.ntiles;

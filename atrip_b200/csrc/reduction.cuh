@@ -16,6 +16,7 @@
 // fixed order, so results are run-to-run deterministic and there is no per-tuple DtoH.
 #pragma once
 #include "common.cuh"
+#include "contraction.cuh"
 #include "schedule.hpp"
 
 namespace ab {
@@ -29,7 +30,8 @@ struct ReduceParams {
   int No, Nv;
   int ntuples;
   const TupleRec *recs;  // the batch: tuple + store slots (vij: Vabij blocks of (b,c) (a,c) (a,b))
-  const double *R;    // class cubes giving Tijk           [ntuples][3][No^3]
+  const double *R;    // class cubes giving Tijk           [ntuples][3][cube_stride], 8x8x8-blocked
+  size_t cube_stride; // cube_blocked_elems(No)
   const double *RZ;   // class cubes giving the Tijk inside Zijk (== R except in the cT pass)
   const double *eps_i, *eps_a, *Tai;
   const double *VIJ;  // owned Vabij pair blocks [slot][No^2]
@@ -65,8 +67,8 @@ reduce_kernel(const ReduceParams P) {
   }
   const int a = rec.a, b = rec.b, c = rec.c;
   const int No = P.No, Nv = P.Nv;
-  const size_t NoNo = (size_t)No * No, cube = NoNo * No;
-  // the three class cubes of kernel 1, all indexed [i + j No + k No^2]
+  const size_t NoNo = (size_t)No * No, cube = P.cube_stride;
+  // the three class cubes of kernel 1, all at Tijk's (i,j,k), stored as contiguous 8x8x8 tiles
   const double *Ck = P.R + (size_t)tup * 3 * cube, *Cj = Ck + cube, *Ci = Cj + cube;
   const double *Zk = P.RZ + (size_t)tup * 3 * cube, *Zj = Zk + cube, *Zi = Zj + cube;
   const double *Vmat[3];  // VBCij, VACij, VABij
@@ -107,12 +109,13 @@ reduce_kernel(const ReduceParams P) {
         double lk[6][2], lj[6][2], li[6][2];
 #pragma unroll
         for (int p = 0; p < 6; p++) {
-          const int x = blk[PX[p]] * RT + l0, y = blk[PY[p]] * RT + l1;
+          // tile (blk[PX], blk[PY], blk[PZ]) is 512 contiguous doubles: thread tid takes elements
+          // tid and tid + 256, i.e. (x,y,z) = (l0, l1, l2 + 4 it) -- full-line coalesced loads
+          const size_t tb = (((size_t)blk[PZ[p]] * nb + blk[PY[p]]) * nb + blk[PX[p]]) * 512 + tid;
 #pragma unroll
           for (int it = 0; it < 2; it++) {
-            const int z = blk[PZ[p]] * RT + l2 + 4 * it;
-            const bool ok = canon[p] == p && x < No && y < No && z < No;
-            const size_t idx = ok ? x + (size_t)y * No + (size_t)z * NoNo : 0;
+            const bool ok = canon[p] == p;
+            const size_t idx = ok ? tb + 256 * it : 0;
             lk[p][it] = ok ? Ck[idx] : 0.0;
             lj[p][it] = ok ? Cj[idx] : 0.0;
             li[p][it] = ok ? Ci[idx] : 0.0;
@@ -141,17 +144,13 @@ reduce_kernel(const ReduceParams P) {
           if (tid + REDUCE_THREADS * q < 18 * 64) Vb[tid + REDUCE_THREADS * q] = lv[q];
         if (CT) {  // (cT): Zijk comes from the V-pass cubes, Tijk (above) from the J pass
 #pragma unroll
-          for (int p = 0; p < 6; p++) {
-            const int x = blk[PX[p]] * RT + l0, y = blk[PY[p]] * RT + l1;
+          for (int p = 0; p < 6; p++)
+            if (canon[p] == p) {
+              const size_t tb = (((size_t)blk[PZ[p]] * nb + blk[PY[p]]) * nb + blk[PX[p]]) * 512 + tid;
 #pragma unroll
-            for (int it = 0; it < 2; it++) {
-              const int z = blk[PZ[p]] * RT + l2 + 4 * it;
-              const bool ok = canon[p] == p && x < No && y < No && z < No;
-              const size_t idx = ok ? x + (size_t)y * No + (size_t)z * NoNo : 0;
-              const double wz = ok ? (Zk[idx] + Zj[idx]) + Zi[idx] : 0.0;
-              if (canon[p] == p) Zt[p * RTILE + l0 + RS1 * l1 + RS2 * (l2 + 4 * it)] = wz;
+              for (int it = 0; it < 2; it++)
+                Zt[p * RTILE + l0 + RS1 * l1 + RS2 * (l2 + 4 * it)] = (Zk[tb + 256 * it] + Zj[tb + 256 * it]) + Zi[tb + 256 * it];
             }
-          }
         }
         __syncthreads();
         // ---- energy of the (i in I, j in J, k in K) points with k <= j <= i
@@ -234,14 +233,15 @@ __global__ void cubes_kernel(const ReduceParams P, int tup, double *Tijk, double
   const size_t NoNo = (size_t)No * No, cube = NoNo * No;
   const TupleRec rec = P.recs[tup];
   const int3 abc = make_int3(rec.a, rec.b, rec.c);
-  const double *Ck = P.R + (size_t)tup * 3 * cube, *Cj = Ck + cube, *Ci = Cj + cube;
+  const double *Ck = P.R + (size_t)tup * 3 * P.cube_stride, *Cj = Ck + P.cube_stride, *Ci = Cj + P.cube_stride;
   const double *Vm[3];
   for (int q = 0; q < 3; q++)
     Vm[q] = rec.vij[q] >= P.ownedV ? P.VIJc + (size_t)(rec.vij[q] - P.ownedV) * NoNo : P.VIJ + (size_t)rec.vij[q] * NoNo;
   const double *Vbc = Vm[0], *Vac = Vm[1], *Vab = Vm[2];
   for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < cube; e += (size_t)gridDim.x * blockDim.x) {
     const int i = (int)(e % No), j = (int)((e / No) % No), k = (int)(e / NoNo);
-    const double w = (Ck[e] + Cj[e]) + Ci[e];  // the class cubes share Tijk's index order
+    const size_t o = cube_offset(No, i, j, k);  // the class cubes share Tijk's (i,j,k)
+    const double w = (Ck[o] + Cj[o]) + Ci[o];
     if (Tijk) Tijk[e] = w;
     if (Zijk)
       Zijk[e] = ((w + P.Tai[abc.x + (size_t)i * Nv] * Vbc[j + (size_t)k * No]) +
