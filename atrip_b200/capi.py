@@ -44,7 +44,8 @@ class Config(C.Structure):
 
 
 def lib_path():
-    return os.path.join(CSRC, "libatrip_b200.so")
+    # ATRIP_B200_LIB: developer A/B builds of the same library (tools/ab_build.sh)
+    return os.environ.get("ATRIP_B200_LIB") or os.path.join(CSRC, "libatrip_b200.so")
 
 
 def build_library(force=False, verbose=False):

@@ -75,7 +75,7 @@ __host__ __device__ inline size_t contract_stage_bytes(int arows, int NI) {
   return (size_t)(arows + NI * 8) * 128;
 }
 
-template <int MI, int NI, int MAXT>
+template <int MI, int NI, int MAXT, bool KTAIL>
 __global__ void __launch_bounds__(MAXT, 1)
 contract_kernel(const __grid_constant__ ContractMaps M, const ContractParams P) {
   extern __shared__ unsigned char smem_raw[];
@@ -189,13 +189,15 @@ contract_kernel(const __grid_constant__ ContractMaps M, const ContractParams P) 
 #pragma unroll
           for (int j = 0; j < NI; j++) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
       };
-      if (ch != P.nk - 1 && ch != nchunks - 1) {
+      if (!KTAIL || (ch != P.nk - 1 && ch != nchunks - 1)) {
 #pragma unroll
         for (int s = 0; s < 4; s++) kstep(cs[s]);
       } else {
-        // last chunk of an operand pair: only the k-steps that hold data (the rest of the
-        // 16-wide chunk is the zero padding of Kp)
-        for (int s = 0; s < P.last_steps; s++) kstep((uint32_t)(((2 * s + (t >> 1)) ^ perm) * 16));
+        // KTAIL: last chunk of an operand pair when Kp > No + Nv -- only the k-steps that hold
+        // data (the rest of the 16-wide chunk is zero padding)
+        kstep(cs[0]);
+        if (P.last_steps > 1) kstep(cs[1]);
+        if (P.last_steps > 2) kstep(cs[2]);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty_bar[stage]);
@@ -208,27 +210,34 @@ contract_kernel(const __grid_constant__ ContractMaps M, const ContractParams P) 
     // the offset is separable, off(i,j,k) = gi(i) + gj(j) + gk(k).
     double *Rc = P.R + ((size_t)tup * 3 + cls) * P.cube_stride;
     const int u0 = (mt % P.utiles) * P.tu, v0 = (mt / P.utiles) * P.tv;
-    const int nb = (P.No + 7) >> 3;
-    auto gi = [&](int i) { return (size_t)(i >> 3) * 512 + (i & 7); };
-    auto gj = [&](int j) { return (size_t)(j >> 3) * nb * 512 + 8 * (j & 7); };
-    auto gk = [&](int k) { return (size_t)(k >> 3) * nb * nb * 512 + 64 * (k & 7); };
+    const unsigned nb = (unsigned)(P.No + 7) >> 3;
+    // tile stride / in-tile stride of the coordinate the column index n plays in this class
+    const unsigned cT = cls == 0 ? nb * nb * 512u : (cls == 1 ? nb * 512u : 512u), cS = cls == 0 ? 64u : (cls == 1 ? 8u : 1u);
+    // ... and of the row coordinates u (fast) and v
+    const unsigned uT = cls == 2 ? nb * 512u : 512u, uS = cls == 2 ? 8u : 1u;
+    const unsigned vT = cls == 0 ? nb * 512u : nb * nb * 512u, vS = cls == 0 ? 8u : 64u;
+    unsigned cb[2];  // column offset of fragment column e at j = 0: col = nt NI 8 + j 8 + pc, pc < 8
+    int pc[2];
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      const int cf = 2 * t + e;
+      pc[e] = 2 * (cf & 3) + (cf >> 2);
+      cb[e] = (unsigned)(nt * NI) * cT + (unsigned)pc[e] * cS;
+    }
     int ul = (warp * MI * 8 + perm) % P.tu, vl = (warp * MI * 8 + perm) / P.tu;
 #pragma unroll
     for (int i = 0; i < MI; i++) {
       const int rl = warp * MI * 8 + i * 8 + perm;
       const int u = u0 + ul, v = v0 + vl;
-      const size_t m = cls == 0 ? gi(u) + gj(v) : (cls == 1 ? gi(u) + gk(v) : gj(u) + gk(v));
+      const unsigned m = (unsigned)(u >> 3) * uT + (unsigned)(u & 7) * uS + (unsigned)(v >> 3) * vT + (unsigned)(v & 7) * vS;
       ul += 8;
       while (ul >= P.tu) { ul -= P.tu; vl++; }
       if (rl < tile_rows && u < P.No && v < P.No) {
 #pragma unroll
         for (int j = 0; j < NI; j++) {
 #pragma unroll
-          for (int e = 0; e < 2; e++) {
-            const int cf = 2 * t + e;
-            const int col = nt * NI * 8 + j * 8 + 2 * (cf & 3) + (cf >> 2);
-            if (col < P.No) Rc[m + (cls == 0 ? gk(col) : (cls == 1 ? gj(col) : gi(col)))] = acc[i][j][e];
-          }
+          for (int e = 0; e < 2; e++)
+            if (nt * NI * 8 + j * 8 + pc[e] < P.No) Rc[m + cb[e] + (unsigned)j * cT] = acc[i][j][e];
         }
       }
     }

@@ -43,9 +43,11 @@ struct Fail {
 // ------------------------------------------------------------------ contraction kernel registry
 struct KernelVariant {
   int MI, NI, maxt;
-  const void *fn;
+  const void *fn, *fn_ktail;  // fn_ktail: skips the zero-padded k-steps when Kp > No + Nv
 };
-#define VARIANT(mi, ni, maxt) KernelVariant{mi, ni, maxt, (const void *)contract_kernel<mi, ni, maxt>}
+#define VARIANT(mi, ni, maxt)                                                       \
+  KernelVariant{mi, ni, maxt, (const void *)contract_kernel<mi, ni, maxt, false>,  \
+                (const void *)contract_kernel<mi, ni, maxt, true>}
 // accumulators take 4*MI*NI registers; the thread cap follows from the 64K register file
 const KernelVariant kVariants[] = {
     VARIANT(2, 1, 512), VARIANT(3, 1, 512), VARIANT(4, 1, 512), VARIANT(5, 1, 512),
@@ -163,7 +165,9 @@ struct atrip_b200_ctx {
   int No = 0, Nv = 0, Kp = 0;
   int nsm = 0;
   size_t smem_limit = 0;
-  cudaStream_t stream = nullptr, xstream = nullptr;  // compute; slice exchange (side stream)
+  // contraction (high priority); reduction of the previous batch (low priority, runs beside the
+  // next contraction on the same SMs); slice exchange (side stream)
+  cudaStream_t stream = nullptr, rstream = nullptr, xstream = nullptr;
   cudaEvent_t ev[6]{};
 
   // stores: owned slices in the layouts of stores.cuh, slot numbering of schedule.hpp
@@ -185,7 +189,8 @@ struct atrip_b200_ctx {
 
   // work buffers
   int batch = 0;
-  double *R = nullptr, *RJ = nullptr, *e_tuple = nullptr, *d_total = nullptr;
+  double *R[2] = {nullptr, nullptr}, *RJ[2] = {nullptr, nullptr};  // class cubes, double-buffered by batch parity
+  double *e_tuple = nullptr, *d_total = nullptr;
   TupleRec *h_recs = nullptr, *d_recs = nullptr;  // [REC_RING][batch]
   cudaEvent_t rec_ev[REC_RING]{};
   uint64_t rec_uses = 0;
@@ -200,6 +205,7 @@ struct atrip_b200_ctx {
   int32_t *h_req_send = nullptr, *h_req_recv = nullptr;   // pinned [2][nranks][req_cap]
   int32_t *d_req_send = nullptr, *d_req_recv = nullptr;
   cudaEvent_t xdone[4]{}, cdone[4]{};
+  cudaEvent_t evV[4]{}, evJ[4]{}, rdone[4]{};               // contraction (V / J pass) and reduction of batch k done
   double *d_reduce = nullptr;                             // all-reduce scratch
   int transport = 0;                                      // 1 NCCL send/recv, 2 P2P pulls (copy engines)
   int comm_sms = 0;                                       // SMs the contraction leaves to NCCL kernels
@@ -321,7 +327,11 @@ void stream_chunks(atrip_b200_ctx *c, const double *host, size_t nchunks, size_t
   CUDA_OK(cudaStreamSynchronize(c->stream));
 }
 
-void launch_contract(atrip_b200_ctx *c, const TupleRec *d_recs, int ntuples, bool useJ) {
+// the padded contraction length has at least one whole k-step (4 kappa) of zeros
+bool has_ktail(const atrip_b200_ctx *c) { return c->Kp - (c->No + c->Nv) >= 4; }
+const void *contract_fn(const atrip_b200_ctx *c) { return has_ktail(c) ? c->plan.k->fn_ktail : c->plan.k->fn; }
+
+void launch_contract(atrip_b200_ctx *c, const TupleRec *d_recs, int ntuples, bool useJ, int buf) {
   ContractParams P;
   P.No = c->No;
   P.Nv = c->Nv;
@@ -340,7 +350,7 @@ void launch_contract(atrip_b200_ctx *c, const TupleRec *d_recs, int ntuples, boo
   P.ownedA = (int)c->owned[KA];
   P.ownedB = (int)c->owned[KB];
   P.recs = d_recs;
-  P.R = useJ ? c->RJ : c->R;
+  P.R = useJ ? c->RJ[buf] : c->R[buf];
   P.cube_stride = cube_blocked_elems(c->No);
   const long long nitems = 3LL * P.mtiles * P.ntiles * ntuples;
   // NCCL transport: leave a few SMs to the send/recv kernels of the side stream, otherwise they
@@ -348,17 +358,17 @@ void launch_contract(atrip_b200_ctx *c, const TupleRec *d_recs, int ntuples, boo
   const int grid = (int)std::min<long long>(c->nsm - c->comm_sms, nitems);
   if (grid <= 0) return;
   void *args[2] = {useJ ? (void *)&c->mapsJ : (void *)&c->maps, (void *)&P};
-  CUDA_OK(cudaLaunchKernel(c->plan.k->fn, dim3(grid), dim3((c->plan.nw + 1) * 32), args, c->plan.smem, c->stream));
+  CUDA_OK(cudaLaunchKernel(contract_fn(c), dim3(grid), dim3((c->plan.nw + 1) * 32), args, c->plan.smem, c->stream));
 }
 
-ReduceParams reduce_params(atrip_b200_ctx *c, const TupleRec *d_recs, int ntuples, bool ct) {
+ReduceParams reduce_params(atrip_b200_ctx *c, const TupleRec *d_recs, int ntuples, bool ct, int buf) {
   ReduceParams P;
   P.No = c->No;
   P.Nv = c->Nv;
   P.ntuples = ntuples;
   P.recs = d_recs;
-  P.R = ct ? c->RJ : c->R;
-  P.RZ = c->R;
+  P.R = ct ? c->RJ[buf] : c->R[buf];
+  P.RZ = c->R[buf];
   P.cube_stride = cube_blocked_elems(c->No);
   P.eps_i = c->eps_i;
   P.eps_a = c->eps_a;
@@ -370,7 +380,7 @@ ReduceParams reduce_params(atrip_b200_ctx *c, const TupleRec *d_recs, int ntuple
   // CTAs per tuple: fill the 2-CTA/SM slots in whole waves (a batch has few tuples when No is
   // large), but keep several orbits per CTA so its prologue (eps, Tai rows) stays amortised
   const int nb = (c->No + RT - 1) / RT, orbits = nb * (nb + 1) * (nb + 2) / 6;
-  const double slots = 2.0 * c->nsm;
+  const double slots = 4.0 * c->nsm;  // 4 CTAs of 128 threads per SM
   int best = 1;
   double best_score = -1;
   for (int ns = 1; ns <= std::min(orbits, 64); ns++) {
@@ -384,15 +394,15 @@ ReduceParams reduce_params(atrip_b200_ctx *c, const TupleRec *d_recs, int ntuple
   return P;
 }
 
-void launch_reduce(atrip_b200_ctx *c, const TupleRec *d_recs, int ntuples, bool ct, double *total) {
+void launch_reduce(atrip_b200_ctx *c, const TupleRec *d_recs, int ntuples, bool ct, int buf, double *total) {
   if (ntuples <= 0) return;
-  ReduceParams P = reduce_params(c, d_recs, ntuples, ct);
+  ReduceParams P = reduce_params(c, d_recs, ntuples, ct, buf);
   const size_t smem = reduce_smem_bytes(c->No, ct);
   const dim3 grid(ntuples, P.nsplit);
-  if (ct) reduce_kernel<true><<<grid, REDUCE_THREADS, smem, c->stream>>>(P);
-  else reduce_kernel<false><<<grid, REDUCE_THREADS, smem, c->stream>>>(P);
+  if (ct) reduce_kernel<true><<<grid, REDUCE_THREADS, smem, c->rstream>>>(P);
+  else reduce_kernel<false><<<grid, REDUCE_THREADS, smem, c->rstream>>>(P);
   CUDA_OK(cudaGetLastError());
-  accumulate_kernel<<<1, 256, 0, c->stream>>>(c->e_tuple, ntuples * P.nsplit, total);
+  accumulate_kernel<<<1, 256, 0, c->rstream>>>(c->e_tuple, ntuples * P.nsplit, total);
   CUDA_OK(cudaGetLastError());
 }
 
@@ -425,20 +435,33 @@ void create_impl(atrip_b200_ctx *c) {
   c->No = (int)cfg.No;
   c->Nv = (int)cfg.Nv;
   c->Kp = (int)((cfg.No + cfg.Nv + KC - 1) / KC * KC);
-  CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  int prio_least = 0, prio_greatest = 0;
+  CUDA_OK(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+  CUDA_OK(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_greatest));
+  CUDA_OK(cudaStreamCreateWithPriority(&c->rstream, cudaStreamNonBlocking, prio_least));
   CUDA_OK(cudaStreamCreateWithFlags(&c->xstream, cudaStreamNonBlocking));
   for (auto &ev : c->ev) CUDA_OK(cudaEventCreate(&ev));
   for (auto &ev : c->rec_ev) CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   for (auto &ev : c->xdone) CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   for (auto &ev : c->cdone) CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  for (auto &ev : c->evV) CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  for (auto &ev : c->evJ) CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  for (auto &ev : c->rdone) CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
 
-  c->plan = plan_contraction(c->No, c->smem_limit);
+  // one reduction CTA (128 threads, <= 128 registers) must fit on an SM beside the contraction CTA
+  // so the reduction of batch k hides under the contraction of batch k+1: leave it its shared memory
+  const size_t reduce_room = reduce_smem_bytes(c->No, cfg.with_J != 0) + 2048;
+  c->plan = plan_contraction(c->No, c->smem_limit - reduce_room);
   REQUIRE(c->plan.k, "no contraction kernel variant fits this No");
-  CUDA_OK(cudaFuncSetAttribute(c->plan.k->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->plan.smem));
+  CUDA_OK(cudaFuncSetAttribute(contract_fn(c), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->plan.smem));
   CUDA_OK(cudaFuncSetAttribute((const void *)reduce_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)reduce_smem_bytes(c->No, false)));
   CUDA_OK(cudaFuncSetAttribute((const void *)reduce_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)reduce_smem_bytes(c->No, true)));
+  // both kernels ask for the largest shared-memory carve-out, otherwise an SM configured for the
+  // contraction alone has no room left for the reduction CTA that should run beside it
+  for (const void *fn : {contract_fn(c), (const void *)reduce_kernel<false>, (const void *)reduce_kernel<true>})
+    CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
 
   // ---- which slices live here: everything (replica) or the slices this rank owns
   const int sn = (cfg.resident || cfg.nranks == 1) ? 1 : cfg.nranks;
@@ -521,8 +544,10 @@ void create_impl(atrip_b200_ctx *c) {
     batch = std::min<long long>(batch, std::max<long long>(16, (1LL << 30) / (long long)(cube3 * 8)));
   }
   c->batch = (int)std::max<long long>(1, batch);
-  c->R = dalloc<double>(cube3 * c->batch);
-  if (cfg.with_J) c->RJ = dalloc<double>(cube3 * c->batch);
+  for (int b = 0; b < 2; b++) {
+    c->R[b] = dalloc<double>(cube3 * c->batch);
+    if (cfg.with_J) c->RJ[b] = dalloc<double>(cube3 * c->batch);
+  }
   c->e_tuple = dalloc<double>((size_t)c->batch * 64);
   c->d_total = dalloc<double>(2);
   c->d_reduce = dalloc<double>(16);
@@ -554,8 +579,9 @@ void destroy_impl(atrip_b200_ctx *c) {
     for (size_t p = 0; p < v.size(); p++)
       if (v[p] && (int)p != c->cfg.rank) cudaIpcCloseMemHandle(v[p]);
   if (c->comm && nccl().ok) nccl().CommDestroy(c->comm);
+  if (c->rstream) cudaStreamSynchronize(c->rstream);
   void *ptrs[] = {c->AX, c->BY, c->VIJ, c->AXJ, c->BYJ, c->eps_i, c->eps_a, c->Tai, c->xtab, c->btab,
-                  c->vtab, c->xlist, c->ylist, c->zlist, c->tflag, c->vy, c->vz, c->R, c->RJ,
+                  c->vtab, c->xlist, c->ylist, c->zlist, c->tflag, c->vy, c->vz, c->R[0], c->R[1], c->RJ[0], c->RJ[1],
                   c->e_tuple, c->d_total, c->d_reduce, c->d_recs, c->d_stage[0], c->d_stage[1],
                   c->cA, c->cB, c->cV, c->cAJ, c->cBJ, c->d_req_send, c->d_req_recv};
   for (void *p : ptrs)
@@ -573,7 +599,11 @@ void destroy_impl(atrip_b200_ctx *c) {
   kill(c->rec_ev, REC_RING);
   kill(c->xdone, 4);
   kill(c->cdone, 4);
+  kill(c->evV, 4);
+  kill(c->evJ, 4);
+  kill(c->rdone, 4);
   if (c->stream) cudaStreamDestroy(c->stream);
+  if (c->rstream) cudaStreamDestroy(c->rstream);
   if (c->xstream) cudaStreamDestroy(c->xstream);
   delete c;
 }
@@ -841,49 +871,63 @@ void run_list(atrip_b200_ctx *c, const Tuple *list, int64_t count, double *energ
     std::memcpy(hr, pl.recs.data(), sizeof(TupleRec) * nt);
     if (sh) CUDA_OK(cudaStreamWaitEvent(c->stream, c->xdone[k & 3], 0));
     CUDA_OK(cudaMemcpyAsync(dr, hr, sizeof(TupleRec) * nt, cudaMemcpyHostToDevice, c->stream));
-    // per-kernel events around the first batches only: contraction [2,3], reduction [3,4]
+    // ---- contraction of batch k on the high-priority stream into cube buffer k % 2 ...
+    const int buf = (int)(k & 1);
+    if (k >= 2) CUDA_OK(cudaStreamWaitEvent(c->stream, c->rdone[(k - 2) & 3], 0));  // buffer reduced
+    // per-kernel events around the first batches only: contraction [2,3], reduction [4,5]
     const bool sample = sampled < 4;
     if (sample) CUDA_OK(cudaEventRecord(c->ev[2], c->stream));
-    launch_contract(c, dr, nt, false);
+    launch_contract(c, dr, nt, false, buf);
     n_contract++;
     if (sample) CUDA_OK(cudaEventRecord(c->ev[3], c->stream));
-    launch_reduce(c, dr, nt, false, c->d_total);
-    n_reduce += 2;
-    if (sample) CUDA_OK(cudaEventRecord(c->ev[4], c->stream));
+    CUDA_OK(cudaEventRecord(c->evV[k & 3], c->stream));
     if (ct) {
-      launch_contract(c, dr, nt, true);
-      launch_reduce(c, dr, nt, true, c->d_total + 1);
+      launch_contract(c, dr, nt, true, buf);
       n_contract++;
+      CUDA_OK(cudaEventRecord(c->evJ[k & 3], c->stream));
+    }
+    CUDA_OK(cudaEventRecord(c->cdone[k & 3], c->stream));
+    // ---- ... and its reduction on the low-priority stream: one 128-thread CTA per SM fits
+    //      beside the persistent contraction CTA of batch k+1, so it costs no time of its own
+    CUDA_OK(cudaStreamWaitEvent(c->rstream, c->evV[k & 3], 0));
+    if (sample) CUDA_OK(cudaEventRecord(c->ev[4], c->rstream));
+    launch_reduce(c, dr, nt, false, buf, c->d_total);
+    n_reduce += 2;
+    if (sample) CUDA_OK(cudaEventRecord(c->ev[5], c->rstream));
+    if (ct) {
+      CUDA_OK(cudaStreamWaitEvent(c->rstream, c->evJ[k & 3], 0));
+      launch_reduce(c, dr, nt, true, buf, c->d_total + 1);
       n_reduce += 2;
     }
-    CUDA_OK(cudaEventRecord(c->rec_ev[slot], c->stream));
-    if (sh) CUDA_OK(cudaEventRecord(c->cdone[k & 3], c->stream));
+    CUDA_OK(cudaEventRecord(c->rdone[k & 3], c->rstream));
+    CUDA_OK(cudaEventRecord(c->rec_ev[slot], c->rstream));
     // ---- next batch: host plan (and, sharded, its exchange on the side stream)
     if (k + 1 < nb) {
       if (!sh) make_plan(k + 1);
       else if (p2p) {  // fully asynchronous: the host never waits for a transfer
         make_plan(k + 1);
-        if (k >= 1) CUDA_OK(cudaStreamWaitEvent(c->xstream, c->cdone[(k - 1) & 3], 0));  // region (k+1)%2 is free
+        if (k >= 1) CUDA_OK(cudaStreamWaitEvent(c->xstream, c->rdone[(k - 1) & 3], 0));  // region (k+1)%2 is free
         pull_step(c, &plans[(k + 1) % 3], (int)((k + 1) & 1));
         CUDA_OK(cudaEventRecord(c->xdone[(k + 1) & 3], c->xstream));
       } else {
         CUDA_OK(cudaEventSynchronize(c->xdone[k & 3]));  // peers' requests for batch k+1 are on the host
         if (k + 2 < nb) make_plan(k + 2);
-        if (k >= 1) CUDA_OK(cudaStreamWaitEvent(c->xstream, c->cdone[(k - 1) & 3], 0));  // region (k+1)%2 is free
+        if (k >= 1) CUDA_OK(cudaStreamWaitEvent(c->xstream, c->rdone[(k - 1) & 3], 0));  // region (k+1)%2 is free
         exchange_step(c, k + 1, &plans[(k + 1) % 3], k + 2 < nb ? &plans[(k + 2) % 3] : nullptr);
         CUDA_OK(cudaEventRecord(c->xdone[(k + 1) & 3], c->xstream));
       }
     }
     if (sample) {
-      CUDA_OK(cudaEventSynchronize(c->ev[4]));
+      CUDA_OK(cudaEventSynchronize(c->ev[5]));
       float a = 0, b = 0;
       CUDA_OK(cudaEventElapsedTime(&a, c->ev[2], c->ev[3]));
-      CUDA_OK(cudaEventElapsedTime(&b, c->ev[3], c->ev[4]));
+      CUDA_OK(cudaEventElapsedTime(&b, c->ev[4], c->ev[5]));
       ms_contract += a;
       ms_reduce += b;
       sampled++;
     }
   }
+  if (nb > 0) CUDA_OK(cudaStreamWaitEvent(c->stream, c->rdone[(nb - 1) & 3], 0));  // the last reduction
   CUDA_OK(cudaEventRecord(c->ev[1], c->stream));
   double tot[2];
   CUDA_OK(cudaMemcpyAsync(tot, c->d_total, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -927,7 +971,7 @@ void tuple_debug_impl(atrip_b200_ctx *c, int64_t a, int64_t b, int64_t cc, doubl
   if (Tijk) dT = dalloc<double>(cube);
   if (Zijk) dZ = dalloc<double>(cube);
   if (Tijk || Zijk) {
-    ReduceParams P = reduce_params(c, c->d_recs + slot * c->batch, 1, false);
+    ReduceParams P = reduce_params(c, c->d_recs + slot * c->batch, 1, false, 0);
     cubes_kernel<<<grid_for(cube, c->nsm), 256, 0, c->stream>>>(P, 0, dT, dZ);
     CUDA_OK(cudaGetLastError());
   }

@@ -22,9 +22,14 @@
 namespace ab {
 
 constexpr int RT = 8;                 // tile edge
-constexpr int RS1 = 9, RS2 = 81;      // padded strides of a tile in shared memory
-constexpr int RTILE = 8 * 81 + 8;     // doubles reserved per tile (>= 7 + 7*9 + 7*81 + 1)
-constexpr int REDUCE_THREADS = 256;
+constexpr int RTILE = 8 * 72;         // doubles per tile in shared memory: z planes padded to 72
+constexpr int REDUCE_THREADS = 128;   // 4 warps: one CTA fits beside a contraction CTA on an SM
+
+// Shared-memory position of tile element (x,y,z): the x index is XOR-swizzled with (y & 6) ^ z and
+// the z planes are padded to 72 doubles.  A half-warp of the compute phase (8 values of i, 2 of
+// j, one k) then hits 16 different 8-byte banks for ALL six index permutations [i,j,k] ... [k,j,i]
+// (ncu r01b: the former [x + 9 y + 81 z] layout replayed every LDS 2.2 times).
+__device__ __forceinline__ int tile_pos(int x, int y, int z) { return (x ^ ((y & 6) ^ z)) + 8 * y + 72 * z; }
 
 struct ReduceParams {
   int No, Nv;
@@ -45,9 +50,8 @@ __host__ __device__ inline size_t reduce_smem_bytes(int No, bool ct) {
   return sizeof(double) * ((size_t)(ct ? 12 : 6) * RTILE + 18 * 64 + 4 * (size_t)No + 32);
 }
 
-
 template <bool CT>
-__global__ void __launch_bounds__(REDUCE_THREADS, 2)
+__global__ void __launch_bounds__(REDUCE_THREADS, 4)
 reduce_kernel(const ReduceParams P) {
   extern __shared__ double sm[];
   double *Wt = sm;                               // [6][RTILE]
@@ -75,7 +79,7 @@ reduce_kernel(const ReduceParams P) {
 #pragma unroll
   for (int q = 0; q < 3; q++)
     Vmat[q] = rec.vij[q] >= P.ownedV ? P.VIJc + (size_t)(rec.vij[q] - P.ownedV) * NoNo : P.VIJ + (size_t)rec.vij[q] * NoNo;
-  for (int i = tid; i < No; i += blockDim.x) {
+  for (int i = tid; i < No; i += REDUCE_THREADS) {
     sEps[i] = P.eps_i[i];
     sTa[i] = P.Tai[a + (size_t)i * Nv];
     sTb[i] = P.Tai[b + (size_t)i * Nv];
@@ -89,7 +93,9 @@ reduce_kernel(const ReduceParams P) {
   constexpr int PX[6] = {0, 0, 1, 1, 2, 2}, PY[6] = {1, 2, 0, 2, 0, 1}, PZ[6] = {2, 1, 2, 0, 1, 0};
   const int nb = (No + RT - 1) / RT;
   double esum = 0.0;
-  const int l0 = tid & 7, l1 = (tid >> 3) & 7, l2 = tid >> 6;  // l2 in 0..3
+  // element e = tid + 128 q of a tile is (x,y,z) = (l0, l1, l2 + 2 q); the same mapping gives
+  // the 4 points (il, jl, kl + 2 q) a thread evaluates
+  const int l0 = tid & 7, l1 = (tid >> 3) & 7, l2 = tid >> 6;  // l2 in 0..1
 
   __syncthreads();  // publishes sEps, sTa, sTb, sTc
   int orbit = -1;
@@ -99,103 +105,103 @@ reduce_kernel(const ReduceParams P) {
         if (++orbit % P.nsplit != split) continue;
         const int blk[3] = {I, J, K};
         // coincident block coordinates give identical tiles: build each distinct one once
-        // (tile p of 0 (I,J,K) 1 (I,K,J) 2 (J,I,K) 3 (J,K,I) 4 (K,I,J) 5 (K,J,I) -> canon[p])
+        // (tile p -> canon[p])
         const bool eIJ = (I == J), eJK = (J == K);
         const int c1 = eJK ? 0 : 1, c2 = eIJ ? 0 : 2, c3 = (eIJ && eJK) ? 0 : (eIJ ? 1 : 3),
                   c4 = (eIJ && eJK) ? 0 : (eJK ? 2 : 4), c5 = (eIJ && eJK) ? 0 : (eIJ ? 4 : (eJK ? 3 : 5));
         const int canon[6] = {0, c1, c2, c3, c4, c5};
         // ---- issue every global load of the orbit before touching shared memory: up to
-        //      6 tiles x 2 points x 3 class cubes per thread in flight (predicated, no branches)
-        double lk[6][2], lj[6][2], li[6][2];
+        //      6 tiles x 4 elements x 3 class cubes per thread in flight (predicated, no branches);
+        //      a tile is 512 contiguous doubles, so these are full-line coalesced loads
+        double lk[6][4], lj[6][4], li[6][4];
 #pragma unroll
         for (int p = 0; p < 6; p++) {
-          // tile (blk[PX], blk[PY], blk[PZ]) is 512 contiguous doubles: thread tid takes elements
-          // tid and tid + 256, i.e. (x,y,z) = (l0, l1, l2 + 4 it) -- full-line coalesced loads
-          const size_t tb = (((size_t)blk[PZ[p]] * nb + blk[PY[p]]) * nb + blk[PX[p]]) * 512 + tid;
+          const bool ok = canon[p] == p;
+          const size_t tb = ok ? (((size_t)blk[PZ[p]] * nb + blk[PY[p]]) * nb + blk[PX[p]]) * 512 + tid : 0;
 #pragma unroll
-          for (int it = 0; it < 2; it++) {
-            const bool ok = canon[p] == p;
-            const size_t idx = ok ? tb + 256 * it : 0;
-            lk[p][it] = ok ? Ck[idx] : 0.0;
-            lj[p][it] = ok ? Cj[idx] : 0.0;
-            li[p][it] = ok ? Ci[idx] : 0.0;
+          for (int q = 0; q < 4; q++) {
+            lk[p][q] = ok ? Ck[tb + 128 * q] : 0.0;
+            lj[p][q] = ok ? Cj[tb + 128 * q] : 0.0;
+            li[p][q] = ok ? Ci[tb + 128 * q] : 0.0;
           }
         }
         // Vabij blocks: Vb[mat][pair(X,Y)][xl + 8 yl] = Vmat[x + y No]
-        double lv[5];
+        double lv[9];
 #pragma unroll
-        for (int q = 0; q < 5; q++) {
-          const int e = tid + REDUCE_THREADS * q;
+        for (int q = 0; q < 9; q++) {
+          const int e = tid + REDUCE_THREADS * q;  // < 18 * 64 = 9 * 128
           const int mat = e / 384, r = e - mat * 384, pr = r >> 6, xl = r & 7, yl = (r >> 3) & 7;
           const int X = pr >> 1, Y = (pr & 1) ? (X == 2 ? 1 : 2) : (X == 0 ? 1 : 0);
           const int x = blk[X] * RT + xl, y = blk[Y] * RT + yl;
-          lv[q] = (e < 18 * 64 && x < No && y < No) ? Vmat[mat < 3 ? mat : 0][x + (size_t)y * No] : 0.0;
+          lv[q] = (x < No && y < No) ? Vmat[mat][x + (size_t)y * No] : 0.0;
         }
         __syncthreads();  // previous orbit fully consumed
 #pragma unroll
         for (int p = 0; p < 6; p++)
           if (canon[p] == p) {
 #pragma unroll
-            for (int it = 0; it < 2; it++)
-              Wt[p * RTILE + l0 + RS1 * l1 + RS2 * (l2 + 4 * it)] = (lk[p][it] + lj[p][it]) + li[p][it];
+            for (int q = 0; q < 4; q++) Wt[p * RTILE + tile_pos(l0, l1, l2 + 2 * q)] = (lk[p][q] + lj[p][q]) + li[p][q];
           }
 #pragma unroll
-        for (int q = 0; q < 5; q++)
-          if (tid + REDUCE_THREADS * q < 18 * 64) Vb[tid + REDUCE_THREADS * q] = lv[q];
+        for (int q = 0; q < 9; q++) Vb[tid + REDUCE_THREADS * q] = lv[q];
         if (CT) {  // (cT): Zijk comes from the V-pass cubes, Tijk (above) from the J pass
 #pragma unroll
           for (int p = 0; p < 6; p++)
             if (canon[p] == p) {
               const size_t tb = (((size_t)blk[PZ[p]] * nb + blk[PY[p]]) * nb + blk[PX[p]]) * 512 + tid;
 #pragma unroll
-              for (int it = 0; it < 2; it++)
-                Zt[p * RTILE + l0 + RS1 * l1 + RS2 * (l2 + 4 * it)] = (Zk[tb + 256 * it] + Zj[tb + 256 * it]) + Zi[tb + 256 * it];
+              for (int q = 0; q < 4; q++)
+                Zt[p * RTILE + tile_pos(l0, l1, l2 + 2 * q)] = (Zk[tb + 128 * q] + Zj[tb + 128 * q]) + Zi[tb + 128 * q];
             }
         }
         __syncthreads();
         // ---- energy of the (i in I, j in J, k in K) points with k <= j <= i
+        const int il = l0, jl = l1;
+        const int i = I * RT + il, j = J * RT + jl;
+        if (i < No && j <= i) {
+          const double *Vbc = Vb, *Vac = Vb + 384, *Vab = Vb + 768;
+          // Vabij pair blocks: 0 (I,J) 1 (I,K) 2 (J,I) 3 (J,K) 4 (K,I) 5 (K,J)
+          const int pij = 0 * 64 + il + 8 * jl, pji = 2 * 64 + jl + 8 * il;
+          const double tai = sTa[i], taj = sTa[j], tbi = sTb[i], tbj = sTb[j], tci = sTc[i], tcj = sTc[j];
+          const double eij = sEps[i] + sEps[j];
+          const double facij = (i == j) ? 0.5 : 1.0;
 #pragma unroll
-        for (int it = 0; it < 2; it++) {
-          const int e = tid + REDUCE_THREADS * it;
-          const int il = e & 7, jl = (e >> 3) & 7, kl = e >> 6;
-          const int i = I * RT + il, j = J * RT + jl, k = K * RT + kl;
-          if (i < No && j <= i && k <= j) {
-            // tiles: 0 (I,J,K) 1 (I,K,J) 2 (J,I,K) 3 (J,K,I) 4 (K,I,J) 5 (K,J,I)
-            const int o0 = il + RS1 * jl + RS2 * kl, o1 = RTILE * c1 + il + RS1 * kl + RS2 * jl;
-            const int o2 = RTILE * c2 + jl + RS1 * il + RS2 * kl, o3 = RTILE * c3 + jl + RS1 * kl + RS2 * il;
-            const int o4 = RTILE * c4 + kl + RS1 * il + RS2 * jl, o5 = RTILE * c5 + kl + RS1 * jl + RS2 * il;
-            const double A = Wt[o0], B = Wt[o1], C = Wt[o2], D = Wt[o3], E = Wt[o4], F = Wt[o5];
-            // Vabij entries; pair blocks: 0 (I,J) 1 (I,K) 2 (J,I) 3 (J,K) 4 (K,I) 5 (K,J)
-            const int pij = 0 * 64 + il + 8 * jl, pik = 1 * 64 + il + 8 * kl, pji = 2 * 64 + jl + 8 * il;
-            const int pjk = 3 * 64 + jl + 8 * kl, pki = 4 * 64 + kl + 8 * il, pkj = 5 * 64 + kl + 8 * jl;
-            const double *Vbc = Vb, *Vac = Vb + 384, *Vab = Vb + 768;
-            const double tai = sTa[i], taj = sTa[j], tak = sTa[k];
-            const double tbi = sTb[i], tbj = sTb[j], tbk = sTb[k];
-            const double tci = sTc[i], tcj = sTc[j], tck = sTc[k];
-            // Z[x,y,z] = T[x,y,z] + Tai[a,x] Vbc[y,z] + Tai[b,y] Vac[x,z] + Tai[c,z] Vab[x,y]
-            // (Equations.cxx:420-422, three separate += in this order)
-            double U = Zt[o0], V = Zt[o1], W = Zt[o2], X = Zt[o3], Y = Zt[o4], Z = Zt[o5];
-            U = ((U + tai * Vbc[pjk]) + tbj * Vac[pik]) + tck * Vab[pij];  // Z[i,j,k]
-            V = ((V + tai * Vbc[pkj]) + tbk * Vac[pij]) + tcj * Vab[pik];  // Z[i,k,j]
-            W = ((W + taj * Vbc[pik]) + tbi * Vac[pjk]) + tck * Vab[pji];  // Z[j,i,k]
-            X = ((X + taj * Vbc[pki]) + tbk * Vac[pji]) + tci * Vab[pjk];  // Z[j,k,i]
-            Y = ((Y + tak * Vbc[pij]) + tbi * Vac[pkj]) + tcj * Vab[pki];  // Z[k,i,j]
-            Z = ((Z + tak * Vbc[pji]) + tbj * Vac[pki]) + tci * Vab[pkj];  // Z[k,j,i]
-            const double facjk = (j == k) ? 0.5 : 1.0, facij = (i == j) ? 0.5 : 1.0;
-            const double den = epsabc - ((sEps[i] + sEps[j]) + sEps[k]);
-            double value;
-            if (!same) {  // get_energy_distinct, Equations.cxx:129-166
-              const double UXY = U + (X + Y), VWZ = V + (W + Z);
-              const double ADE = A + (D + E), BCF = B + (C + F);
-              const double first = A * U + (B * V + (C * W + (D * X + (E * Y + F * Z))));
-              const double second = (UXY - 2.0 * VWZ) * ADE;
-              const double third = (VWZ - 2.0 * UXY) * BCF;
-              value = 3.0 * first + (second + third);
-            } else {  // get_energy_same, Equations.cxx:209-226: cyclic permutations only
-              const double ABC = A + (D + E), UVW = U + (X + Y);
-              value = 3.0 * ((A * U + D * X) + E * Y) - ABC * UVW;
+          for (int q = 0; q < 4; q++) {
+            const int kl = l2 + 2 * q, k = K * RT + kl;
+            if (k <= j) {
+              // tiles: 0 (I,J,K) 1 (I,K,J) 2 (J,I,K) 3 (J,K,I) 4 (K,I,J) 5 (K,J,I)
+              const int o0 = tile_pos(il, jl, kl), o1 = RTILE * c1 + tile_pos(il, kl, jl);
+              const int o2 = RTILE * c2 + tile_pos(jl, il, kl), o3 = RTILE * c3 + tile_pos(jl, kl, il);
+              const int o4 = RTILE * c4 + tile_pos(kl, il, jl), o5 = RTILE * c5 + tile_pos(kl, jl, il);
+              const double A = Wt[o0], B = Wt[o1], C = Wt[o2], D = Wt[o3], E = Wt[o4], F = Wt[o5];
+              const int pik = 1 * 64 + il + 8 * kl, pjk = 3 * 64 + jl + 8 * kl;
+              const int pki = 4 * 64 + kl + 8 * il, pkj = 5 * 64 + kl + 8 * jl;
+              const double tak = sTa[k], tbk = sTb[k], tck = sTc[k];
+              // Z[x,y,z] = T[x,y,z] + Tai[a,x] Vbc[y,z] + Tai[b,y] Vac[x,z] + Tai[c,z] Vab[x,y]
+              // (Equations.cxx:420-422, three separate += in this order)
+              double U = Zt[o0], V = Zt[o1], W = Zt[o2], X = Zt[o3], Y = Zt[o4], Z = Zt[o5];
+              U = ((U + tai * Vbc[pjk]) + tbj * Vac[pik]) + tck * Vab[pij];  // Z[i,j,k]
+              V = ((V + tai * Vbc[pkj]) + tbk * Vac[pij]) + tcj * Vab[pik];  // Z[i,k,j]
+              W = ((W + taj * Vbc[pik]) + tbi * Vac[pjk]) + tck * Vab[pji];  // Z[j,i,k]
+              X = ((X + taj * Vbc[pki]) + tbk * Vac[pji]) + tci * Vab[pjk];  // Z[j,k,i]
+              Y = ((Y + tak * Vbc[pij]) + tbi * Vac[pkj]) + tcj * Vab[pki];  // Z[k,i,j]
+              Z = ((Z + tak * Vbc[pji]) + tbj * Vac[pki]) + tci * Vab[pkj];  // Z[k,j,i]
+              const double facjk = (j == k) ? 0.5 : 1.0;
+              const double den = epsabc - (eij + sEps[k]);
+              double value;
+              if (!same) {  // get_energy_distinct, Equations.cxx:129-166
+                const double UXY = U + (X + Y), VWZ = V + (W + Z);
+                const double ADE = A + (D + E), BCF = B + (C + F);
+                const double first = A * U + (B * V + (C * W + (D * X + (E * Y + F * Z))));
+                const double second = (UXY - 2.0 * VWZ) * ADE;
+                const double third = (VWZ - 2.0 * UXY) * BCF;
+                value = 3.0 * first + (second + third);
+              } else {  // get_energy_same, Equations.cxx:209-226: cyclic permutations only
+                const double ABC = A + (D + E), UVW = U + (X + Y);
+                value = 3.0 * ((A * U + D * X) + E * Y) - ABC * UVW;
+              }
+              esum += ((2.0 * value) / den) * (facjk * facij);
             }
-            esum += ((2.0 * value) / den) * (facjk * facij);
           }
         }
       }
