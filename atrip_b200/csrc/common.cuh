@@ -38,18 +38,6 @@ __device__ __forceinline__ double synth_val(uint64_t key, uint64_t idx, double s
   return __dmul_rn(scale, __dadd_rn(synth_u(key, idx), -0.5));
 }
 
-// Storage of a class cube: 8x8x8 tiles, each 4 KB contiguous ([x + 8 y + 64 z] inside the tile),
-// tiles ordered [X + nb Y + nb^2 Z], nb = ceil(No/8).  Kernel 2 reads whole tiles (full 128-byte
-// lines; a plain [i + j No + k No^2] cube costs it 2x the DRAM traffic, ncu r01b).
-__host__ __device__ inline size_t cube_blocked_elems(int No) {
-  const size_t nb = (size_t)(No + 7) / 8;
-  return nb * nb * nb * 512;
-}
-__host__ __device__ inline size_t cube_offset(int No, int i, int j, int k) {
-  const size_t nb = (size_t)(No + 7) / 8;
-  return (((size_t)(k >> 3) * nb + (j >> 3)) * nb + (i >> 3)) * 512 + (i & 7) + 8 * (j & 7) + 64 * (k & 7);
-}
-
 // ---------------------------------------------------------------------------------------------
 // mbarrier / TMA / DMMA PTX wrappers (sm_100a)
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {

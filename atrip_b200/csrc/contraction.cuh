@@ -22,20 +22,29 @@
 //                    A tile [tu*tv rows x 16] and the B tile [<=NI*8 rows x 16] of each K chunk
 //                    into an nstages-deep ring guarded by full/empty mbarriers; it runs ahead
 //                    across work items so the pipe never drains between tiles.
-//   warps NW+1..+3 : reducers; kernel 2's work (singles + energy) for the PREVIOUS batch
 //   warps 0..NW-1  : consumers; each owns MI x NI DMMA.8x8x4 accumulator fragments
 //                    (rows [w*MI*8, (w+1)*MI*8) of the tile), loads fragments with LDS.64 from
 //                    the swizzled rows (conflict free: fragment row g <-> tile row 2(g%4)+g/4),
 //                    and stores its C fragments straight to the class cube in HBM/L2.
 #pragma once
 #include "common.cuh"
-#include "reduction.cuh"
 #include "schedule.hpp"
 
 namespace ab {
 
 constexpr int MAX_STAGES = 12;
-constexpr int REDUCER_WARPS = 3;  // with 8 consumers + 1 producer: 3 warps on each SM sub-partition
+
+// Storage of a class cube: 8x8x8 tiles, each 4 KB contiguous ([x + 8 y + 64 z] inside the tile),
+// tiles ordered [X + nb Y + nb^2 Z], nb = ceil(No/8).  Kernel 2 reads whole tiles (full 128-byte
+// lines; a plain [i + j No + k No^2] cube costs it 2x the DRAM traffic, ncu r01b).
+__host__ __device__ inline size_t cube_blocked_elems(int No) {
+  const size_t nb = (size_t)(No + 7) / 8;
+  return nb * nb * nb * 512;
+}
+__host__ __device__ inline size_t cube_offset(int No, int i, int j, int k) {
+  const size_t nb = (size_t)(No + 7) / 8;
+  return (((size_t)(k >> 3) * nb + (j >> 3)) * nb + (i >> 3)) * 512 + (i & 7) + 8 * (j & 7) + 64 * (k & 7);
+}
 
 // tensor maps of the owned stores and of the fetch caches (same layouts; a rank that stores
 // everything passes the owned maps twice)
@@ -60,11 +69,6 @@ struct ContractParams {
   const TupleRec *recs;    // the batch: tuple + store slots of its slices (built on the host)
   double *R;               // [ntuples][3][cube_stride] class cubes C_k, C_j, C_i (8x8x8-blocked)
   size_t cube_stride;      // doubles per stored cube = ceil(No/8)^3 * 512
-  // reduction job of the PREVIOUS batch, done by the three reducer warps of every CTA while the
-  // consumer warps contract this batch (r_items = 0: none)
-  ReduceParams rp;
-  int r_items;             // rp.ntuples * rp.nsplit (tuple, orbit split) items
-  int r_ct;                // (cT) form: Tijk from rp.R, Zijk from rp.RZ
 };
 
 __host__ __device__ inline size_t contract_stage_bytes(int arows, int NI) {
@@ -77,7 +81,7 @@ contract_kernel(const __grid_constant__ ContractMaps M, const ContractParams P) 
   extern __shared__ unsigned char smem_raw[];
   __shared__ uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES];
 
-  const int nwarps = (blockDim.x >> 5) - 1 - REDUCER_WARPS;  // consumer warps
+  const int nwarps = (blockDim.x >> 5) - 1;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   unsigned char *base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const size_t stage_bytes = contract_stage_bytes(P.arows, NI);
@@ -107,20 +111,6 @@ contract_kernel(const __grid_constant__ ContractMaps M, const ContractParams P) 
   int stage = 0;
   uint32_t phase = 0;
 
-  if (warp > nwarps) {
-    // ------------------------------------------------------------------ reducers
-    // Kernel 2's work for the previous batch (reduction.cuh), hidden under this batch's DMMA
-    // work: the reducers are latency bound and use the FP64/LSU slots the tensor warps leave.
-    const int rtid = threadIdx.x - (nwarps + 1) * 32;
-    double *rsm = reinterpret_cast<double *>(base + stage_bytes * P.nstages);
-    auto rsync = [] { asm volatile("bar.sync 1, %0;" ::"n"(REDUCER_WARPS * 32) : "memory"); };
-    for (int it = blockIdx.x; it < P.r_items; it += gridDim.x) {
-      const int rt = it / P.rp.nsplit, rs = it - rt * P.rp.nsplit;
-      if (P.r_ct) reduce_item<true, REDUCER_WARPS * 32>(P.rp, rt, rs, rsm, rtid, rsync);
-      else reduce_item<false, REDUCER_WARPS * 32>(P.rp, rt, rs, rsm, rtid, rsync);
-    }
-    return;
-  }
   if (warp == nwarps) {
     // ------------------------------------------------------------------ producer
     if (lane == 0) {

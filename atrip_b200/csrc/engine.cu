@@ -48,19 +48,18 @@ struct KernelVariant {
 #define VARIANT(mi, ni, maxt)                                                       \
   KernelVariant{mi, ni, maxt, (const void *)contract_kernel<mi, ni, maxt, false>,  \
                 (const void *)contract_kernel<mi, ni, maxt, true>}
-// accumulators take 4*MI*NI registers; the thread cap (consumer warps + 1 producer warp + 3
-// reducer warps) follows from the 64K register file
+// accumulators take 4*MI*NI registers; the thread cap follows from the 64K register file
 const KernelVariant kVariants[] = {
     VARIANT(2, 1, 512), VARIANT(3, 1, 512), VARIANT(4, 1, 512), VARIANT(5, 1, 512),
     VARIANT(2, 2, 512), VARIANT(3, 2, 512), VARIANT(4, 2, 512), VARIANT(5, 2, 512),
     VARIANT(2, 3, 512), VARIANT(3, 3, 512), VARIANT(4, 3, 512), VARIANT(5, 3, 512),
     VARIANT(2, 4, 512), VARIANT(3, 4, 512), VARIANT(4, 4, 512), VARIANT(5, 4, 416),
-    VARIANT(2, 5, 512), VARIANT(3, 5, 512), VARIANT(4, 5, 416), VARIANT(5, 5, 384),
-    VARIANT(2, 6, 512), VARIANT(3, 6, 416), VARIANT(4, 6, 384), VARIANT(5, 6, 384),
-    VARIANT(2, 7, 512), VARIANT(3, 7, 416), VARIANT(4, 7, 384),
-    VARIANT(2, 8, 512), VARIANT(3, 8, 416), VARIANT(4, 8, 384),
-    VARIANT(2, 10, 416), VARIANT(3, 10, 384),
-    VARIANT(2, 13, 384),
+    VARIANT(2, 5, 512), VARIANT(3, 5, 512), VARIANT(4, 5, 416), VARIANT(5, 5, 288),
+    VARIANT(2, 6, 512), VARIANT(3, 6, 416), VARIANT(4, 6, 288), VARIANT(5, 6, 288),
+    VARIANT(2, 7, 512), VARIANT(3, 7, 416), VARIANT(4, 7, 288),
+    VARIANT(2, 8, 512), VARIANT(3, 8, 416), VARIANT(4, 8, 288),
+    VARIANT(2, 10, 416), VARIANT(3, 10, 288),
+    VARIANT(2, 13, 288),
 };
 
 struct ContractPlan {
@@ -81,7 +80,7 @@ ContractPlan plan_contraction(int No, size_t smem_limit) {
   double best_score = -1;
   for (const auto &k : kVariants) {
     const int ntiles = (No + k.NI * 8 - 1) / (k.NI * 8);
-    for (int nw = 4; nw <= k.maxt / 32 - 1 - REDUCER_WARPS; nw++) {
+    for (int nw = 4; nw <= k.maxt / 32 - 1; nw++) {
       const int arows = nw * k.MI * 8;
       const size_t stage = contract_stage_bytes(arows, k.NI);
       const int nstages = (int)std::min<size_t>(MAX_STAGES, (smem_limit - 2048) / stage);
@@ -160,14 +159,15 @@ T *dalloc(size_t n) {
 }  // namespace
 
 constexpr int REC_RING = 4;  // batches the host may run ahead of the device
-constexpr int NREGION = 3;   // fetch-cache regions: batch k uses region k % 3
 
 struct atrip_b200_ctx {
   atrip_b200_config cfg{};
   int No = 0, Nv = 0, Kp = 0;
   int nsm = 0;
   size_t smem_limit = 0;
-  cudaStream_t stream = nullptr, xstream = nullptr;  // compute; slice exchange (side stream)
+  // contraction (high priority); reduction of the previous batch (low priority, runs beside the
+  // next contraction on the same SMs); slice exchange (side stream)
+  cudaStream_t stream = nullptr, rstream = nullptr, xstream = nullptr;
   cudaEvent_t ev[6]{};
 
   // stores: owned slices in the layouts of stores.cuh, slot numbering of schedule.hpp
@@ -180,7 +180,7 @@ struct atrip_b200_ctx {
   int *xlist = nullptr, *ylist = nullptr, *zlist = nullptr, *tflag = nullptr, *vy = nullptr, *vz = nullptr;
   bool have_J = false;
 
-  // fetch caches (sharded stores only): NREGION regions of cap[kind] slots, batch k uses region k % 3
+  // fetch caches (sharded stores only): two regions of cap[kind] slots, used by alternate batches
   int64_t cap[3] = {0, 0, 0};
   double *cA = nullptr, *cB = nullptr, *cV = nullptr, *cAJ = nullptr, *cBJ = nullptr;
 
@@ -205,6 +205,7 @@ struct atrip_b200_ctx {
   int32_t *h_req_send = nullptr, *h_req_recv = nullptr;   // pinned [2][nranks][req_cap]
   int32_t *d_req_send = nullptr, *d_req_recv = nullptr;
   cudaEvent_t xdone[4]{}, cdone[4]{};
+  cudaEvent_t evV[4]{}, evJ[4]{}, rdone[4]{};               // contraction (V / J pass) and reduction of batch k done
   double *d_reduce = nullptr;                             // all-reduce scratch
   int transport = 0;                                      // 1 NCCL send/recv, 2 P2P pulls (copy engines)
   int comm_sms = 0;                                       // SMs the contraction leaves to NCCL kernels
@@ -218,7 +219,6 @@ struct atrip_b200_ctx {
   cudaEvent_t stage_ev[2]{};
 
   double timing[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  std::vector<cudaEvent_t> trace;  // ATRIP_B200_TRACE=n: start/end events of the first n batches
 };
 
 namespace {
@@ -252,11 +252,11 @@ void build_maps(atrip_b200_ctx *c, double *AX, uint64_t nA, double *BY, uint64_t
 // (re)build all tensor maps: owned stores, and the fetch caches when there are any
 void build_all_maps(atrip_b200_ctx *c) {
   build_maps(c, c->AX, c->owned[KA], c->BY, c->owned[KB], &c->maps.A, &c->maps.AT, &c->maps.B);
-  if (c->cA) build_maps(c, c->cA, NREGION * c->cap[KA], c->cB, NREGION * c->cap[KB], &c->maps.Ac, &c->maps.ATc, &c->maps.Bc);
+  if (c->cA) build_maps(c, c->cA, 2 * c->cap[KA], c->cB, 2 * c->cap[KB], &c->maps.Ac, &c->maps.ATc, &c->maps.Bc);
   else { c->maps.Ac = c->maps.A; c->maps.ATc = c->maps.AT; c->maps.Bc = c->maps.B; }
   if (c->cfg.with_J) {
     build_maps(c, c->AXJ, c->owned[KA], c->BYJ, c->owned[KB], &c->mapsJ.A, &c->mapsJ.AT, &c->mapsJ.B);
-    if (c->cAJ) build_maps(c, c->cAJ, NREGION * c->cap[KA], c->cBJ, NREGION * c->cap[KB], &c->mapsJ.Ac, &c->mapsJ.ATc, &c->mapsJ.Bc);
+    if (c->cAJ) build_maps(c, c->cAJ, 2 * c->cap[KA], c->cBJ, 2 * c->cap[KB], &c->mapsJ.Ac, &c->mapsJ.ATc, &c->mapsJ.Bc);
     else { c->mapsJ.Ac = c->mapsJ.A; c->mapsJ.ATc = c->mapsJ.AT; c->mapsJ.Bc = c->mapsJ.B; }
   }
 }
@@ -274,12 +274,12 @@ void ensure_caches(atrip_b200_ctx *c, const int64_t need[3]) {
   for (double **p : {&c->cA, &c->cB, &c->cV, &c->cAJ, &c->cBJ})
     if (*p) { cudaFree(*p); *p = nullptr; }
   for (int k = 0; k < 3; k++) c->cap[k] = std::max(c->cap[k], want[k]);
-  c->cA = dalloc<double>(NREGION * c->cap[KA] * slice_elems(c, KA));
-  c->cB = dalloc<double>(NREGION * c->cap[KB] * slice_elems(c, KB));
-  c->cV = dalloc<double>(NREGION * c->cap[KV] * slice_elems(c, KV));
+  c->cA = dalloc<double>(2 * c->cap[KA] * slice_elems(c, KA));
+  c->cB = dalloc<double>(2 * c->cap[KB] * slice_elems(c, KB));
+  c->cV = dalloc<double>(2 * c->cap[KV] * slice_elems(c, KV));
   if (c->cfg.with_J) {
-    c->cAJ = dalloc<double>(NREGION * c->cap[KA] * slice_elems(c, KA));
-    c->cBJ = dalloc<double>(NREGION * c->cap[KB] * slice_elems(c, KB));
+    c->cAJ = dalloc<double>(2 * c->cap[KA] * slice_elems(c, KA));
+    c->cBJ = dalloc<double>(2 * c->cap[KB] * slice_elems(c, KB));
   }
   build_all_maps(c);
 }
@@ -331,16 +331,7 @@ void stream_chunks(atrip_b200_ctx *c, const double *host, size_t nchunks, size_t
 bool has_ktail(const atrip_b200_ctx *c) { return c->Kp - (c->No + c->Nv) >= 4; }
 const void *contract_fn(const atrip_b200_ctx *c) { return has_ktail(c) ? c->plan.k->fn_ktail : c->plan.k->fn; }
 
-ReduceParams reduce_params(atrip_b200_ctx *c, const TupleRec *d_recs, int ntuples, bool ct, int buf);
-
-// One fused launch: the consumer warps contract batch `d_recs` (V or J stores) into cube buffer
-// `buf`, the reducer warps evaluate the reduction job `job` of the previous batch (may be null).
-struct ReduceJob {
-  const TupleRec *recs;
-  int ntuples, buf;
-  bool ct;
-};
-void launch_contract(atrip_b200_ctx *c, const TupleRec *d_recs, int ntuples, bool useJ, int buf, const ReduceJob *job) {
+void launch_contract(atrip_b200_ctx *c, const TupleRec *d_recs, int ntuples, bool useJ, int buf) {
   ContractParams P;
   P.No = c->No;
   P.Nv = c->Nv;
@@ -361,23 +352,13 @@ void launch_contract(atrip_b200_ctx *c, const TupleRec *d_recs, int ntuples, boo
   P.recs = d_recs;
   P.R = useJ ? c->RJ[buf] : c->R[buf];
   P.cube_stride = cube_blocked_elems(c->No);
-  P.r_items = 0;
-  P.r_ct = 0;
-  if (job && job->ntuples > 0) {
-    P.rp = reduce_params(c, job->recs, job->ntuples, job->ct, job->buf);
-    P.r_items = job->ntuples * P.rp.nsplit;
-    P.r_ct = job->ct;
-  } else {
-    P.rp = ReduceParams{};
-  }
   const long long nitems = 3LL * P.mtiles * P.ntiles * ntuples;
   // NCCL transport: leave a few SMs to the send/recv kernels of the side stream, otherwise they
   // only run in the gaps between two persistent contraction launches
-  const int grid = (int)std::min<long long>(c->nsm - c->comm_sms, std::max<long long>(nitems, P.r_items));
+  const int grid = (int)std::min<long long>(c->nsm - c->comm_sms, nitems);
   if (grid <= 0) return;
   void *args[2] = {useJ ? (void *)&c->mapsJ : (void *)&c->maps, (void *)&P};
-  CUDA_OK(cudaLaunchKernel(contract_fn(c), dim3(grid), dim3((c->plan.nw + 1 + REDUCER_WARPS) * 32), args, c->plan.smem,
-                           c->stream));
+  CUDA_OK(cudaLaunchKernel(contract_fn(c), dim3(grid), dim3((c->plan.nw + 1) * 32), args, c->plan.smem, c->stream));
 }
 
 ReduceParams reduce_params(atrip_b200_ctx *c, const TupleRec *d_recs, int ntuples, bool ct, int buf) {
@@ -413,24 +394,16 @@ ReduceParams reduce_params(atrip_b200_ctx *c, const TupleRec *d_recs, int ntuple
   return P;
 }
 
-// partial energies of a reduced batch -> running total (fixed order, stays on the device)
-void launch_accumulate(atrip_b200_ctx *c, int ntuples, bool ct, int buf, double *total) {
-  if (ntuples <= 0) return;
-  const ReduceParams P = reduce_params(c, nullptr, ntuples, ct, buf);
-  accumulate_kernel<<<1, 256, 0, c->stream>>>(c->e_tuple, ntuples * P.nsplit, total);
-  CUDA_OK(cudaGetLastError());
-}
-
-// standalone reduction (last batch of a run: no later contraction launch to hide under)
 void launch_reduce(atrip_b200_ctx *c, const TupleRec *d_recs, int ntuples, bool ct, int buf, double *total) {
   if (ntuples <= 0) return;
   ReduceParams P = reduce_params(c, d_recs, ntuples, ct, buf);
   const size_t smem = reduce_smem_bytes(c->No, ct);
   const dim3 grid(ntuples, P.nsplit);
-  if (ct) reduce_kernel<true><<<grid, REDUCE_THREADS, smem, c->stream>>>(P);
-  else reduce_kernel<false><<<grid, REDUCE_THREADS, smem, c->stream>>>(P);
+  if (ct) reduce_kernel<true><<<grid, REDUCE_THREADS, smem, c->rstream>>>(P);
+  else reduce_kernel<false><<<grid, REDUCE_THREADS, smem, c->rstream>>>(P);
   CUDA_OK(cudaGetLastError());
-  launch_accumulate(c, ntuples, ct, buf, total);
+  accumulate_kernel<<<1, 256, 0, c->rstream>>>(c->e_tuple, ntuples * P.nsplit, total);
+  CUDA_OK(cudaGetLastError());
 }
 
 template <typename T>
@@ -462,30 +435,34 @@ void create_impl(atrip_b200_ctx *c) {
   c->No = (int)cfg.No;
   c->Nv = (int)cfg.Nv;
   c->Kp = (int)((cfg.No + cfg.Nv + KC - 1) / KC * KC);
-  CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  int prio_least = 0, prio_greatest = 0;
+  CUDA_OK(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+  CUDA_OK(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_greatest));
+  CUDA_OK(cudaStreamCreateWithPriority(&c->rstream, cudaStreamNonBlocking, prio_least));
   CUDA_OK(cudaStreamCreateWithFlags(&c->xstream, cudaStreamNonBlocking));
   for (auto &ev : c->ev) CUDA_OK(cudaEventCreate(&ev));
   for (auto &ev : c->rec_ev) CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   for (auto &ev : c->xdone) CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   for (auto &ev : c->cdone) CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  for (auto &ev : c->evV) CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  for (auto &ev : c->evJ) CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  for (auto &ev : c->rdone) CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
 
-  // the reducer warps of the contraction kernel (reduction of the previous batch) need their
-  // shared memory next to the TMA ring
-  const size_t reduce_room = reduce_smem_bytes(c->No, cfg.with_J != 0);
+  // one reduction CTA (128 threads, <= 128 registers) must fit on an SM beside the contraction CTA
+  // so the reduction of batch k hides under the contraction of batch k+1: leave it its shared memory
+  const size_t reduce_room = reduce_smem_bytes(c->No, cfg.with_J != 0) + 2048;
   c->plan = plan_contraction(c->No, c->smem_limit - reduce_room);
-  REQUIRE(c->plan.k, "no contraction kernel variant fits this No");
-  c->plan.smem += reduce_room;
   REQUIRE(c->plan.k, "no contraction kernel variant fits this No");
   CUDA_OK(cudaFuncSetAttribute(contract_fn(c), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->plan.smem));
   CUDA_OK(cudaFuncSetAttribute((const void *)reduce_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)reduce_smem_bytes(c->No, false)));
   CUDA_OK(cudaFuncSetAttribute((const void *)reduce_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)reduce_smem_bytes(c->No, true)));
+  // both kernels ask for the largest shared-memory carve-out, otherwise an SM configured for the
+  // contraction alone has no room left for the reduction CTA that should run beside it
+  for (const void *fn : {contract_fn(c), (const void *)reduce_kernel<false>, (const void *)reduce_kernel<true>})
+    CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
 
-  if (const char *e = std::getenv("ATRIP_B200_TRACE")) {
-    c->trace.resize((size_t)std::max(0, std::min(256, std::atoi(e))) * 4);
-    for (auto &ev : c->trace) CUDA_OK(cudaEventCreate(&ev));
-  }
   // ---- which slices live here: everything (replica) or the slices this rank owns
   const int sn = (cfg.resident || cfg.nranks == 1) ? 1 : cfg.nranks;
   REQUIRE(cfg.transport >= 0 && cfg.transport <= 2, "transport must be 0 (default), 1 (NCCL) or 2 (P2P)");
@@ -602,6 +579,7 @@ void destroy_impl(atrip_b200_ctx *c) {
     for (size_t p = 0; p < v.size(); p++)
       if (v[p] && (int)p != c->cfg.rank) cudaIpcCloseMemHandle(v[p]);
   if (c->comm && nccl().ok) nccl().CommDestroy(c->comm);
+  if (c->rstream) cudaStreamSynchronize(c->rstream);
   void *ptrs[] = {c->AX, c->BY, c->VIJ, c->AXJ, c->BYJ, c->eps_i, c->eps_a, c->Tai, c->xtab, c->btab,
                   c->vtab, c->xlist, c->ylist, c->zlist, c->tflag, c->vy, c->vz, c->R[0], c->R[1], c->RJ[0], c->RJ[1],
                   c->e_tuple, c->d_total, c->d_reduce, c->d_recs, c->d_stage[0], c->d_stage[1],
@@ -621,8 +599,11 @@ void destroy_impl(atrip_b200_ctx *c) {
   kill(c->rec_ev, REC_RING);
   kill(c->xdone, 4);
   kill(c->cdone, 4);
-
+  kill(c->evV, 4);
+  kill(c->evJ, 4);
+  kill(c->rdone, 4);
   if (c->stream) cudaStreamDestroy(c->stream);
+  if (c->rstream) cudaStreamDestroy(c->rstream);
   if (c->xstream) cudaStreamDestroy(c->xstream);
   delete c;
 }
@@ -749,7 +730,7 @@ double *cache_of(const atrip_b200_ctx *c, int kind, bool J) {
 // time): inside one NCCL group
 //   data     for batch `k`:  send the ranges every peer asked of me (peer_req, host copy of the
 //            request lists received one step earlier), receive the ranges of my own plan into
-//            cache region k % 3;
+//            cache region k % 2;
 //   requests for batch k+1:  send my request lists (next != nullptr), receive the peers'.
 // k = -1 is the bootstrap step that only exchanges the request lists of batch 0.
 void exchange_step(atrip_b200_ctx *c, int64_t k, const BatchPlan *mine, const BatchPlan *next) {
@@ -782,7 +763,7 @@ void exchange_step(atrip_b200_ctx *c, int64_t k, const BatchPlan *mine, const Ba
       }
       for (const FetchRange &fr : mine->fetch[(size_t)p]) {
         const size_t el = slice_elems(c, fr.kind);
-        const size_t dst = (size_t)((k % NREGION) * c->cap[fr.kind] + fr.dst_slot) * el;
+        const size_t dst = (size_t)(par * c->cap[fr.kind] + fr.dst_slot) * el;
         NCCL_OK(N.Recv(cache_of(c, fr.kind, false) + dst, (size_t)fr.count * el, ncclFloat64, p, c->comm, c->xstream));
         if (J && fr.kind != KV)
           NCCL_OK(N.Recv(cache_of(c, fr.kind, true) + dst, (size_t)fr.count * el, ncclFloat64, p, c->comm, c->xstream));
@@ -833,11 +814,8 @@ void pull_step(atrip_b200_ctx *c, const BatchPlan *mine, int par) {
 }
 
 // Runs the tuples list[0..count) in device batches.  Replaces the main loop, Atrip.cxx:686-1057.
-// Launch k contracts batch k (consumer warps) and reduces batch k-1 (reducer warps of the same
-// CTAs); the last batch is reduced by the standalone kernel.  Sharded stores: the slices of batch
-// k+1 travel on the side stream while launch k runs (three cache regions: batch k-1's Vabij
-// blocks are still being read by the reducers of launch k).  With the NCCL transport the call is
-// COLLECTIVE -- every rank calls with the same count.
+// Sharded stores: COLLECTIVE -- every rank calls with the same count; slices of batch k+1 travel
+// on the side stream while batch k computes (two cache regions).
 void run_list(atrip_b200_ctx *c, const Tuple *list, int64_t count, double *energy, double *ct_energy) {
   const bool ct = c->have_J;
   const bool sh = sharded(c);
@@ -845,10 +823,13 @@ void run_list(atrip_b200_ctx *c, const Tuple *list, int64_t count, double *energ
   REQUIRE(!sh || c->transport != 2 || !c->peer[0].empty(), "peer stores are not mapped");
   const int64_t nb = (count + c->batch - 1) / c->batch;
   auto nt_of = [&](int64_t k) { return (size_t)std::min<int64_t>(c->batch, count - k * c->batch); };
+  auto base_of = [&](int64_t k, int64_t base[3]) {
+    for (int q = 0; q < 3; q++) base[q] = c->owned[q] + (sh ? (k & 1) * c->cap[q] : 0);
+  };
   BatchPlan plans[3];
   auto make_plan = [&](int64_t k) {
     int64_t base[3];
-    for (int q = 0; q < 3; q++) base[q] = c->owned[q] + (sh ? (k % NREGION) * c->cap[q] : 0);
+    base_of(k, base);
     BatchPlan &pl = plans[k % 3];
     plan_batch(c->map, list + k * c->batch, nt_of(k), base, pl);
     for (int q = 0; q < 3; q++)
@@ -879,8 +860,6 @@ void run_list(atrip_b200_ctx *c, const Tuple *list, int64_t count, double *energ
     }
     CUDA_OK(cudaEventRecord(c->xdone[0], c->xstream));
   }
-  ReduceJob prev{nullptr, 0, 0, false};  // the batch whose cubes wait to be reduced
-  int prev_slot = -1;
   for (int64_t k = 0; k < nb; k++) {
     const int nt = (int)nt_of(k);
     const BatchPlan &pl = plans[k % 3];
@@ -892,71 +871,63 @@ void run_list(atrip_b200_ctx *c, const Tuple *list, int64_t count, double *energ
     std::memcpy(hr, pl.recs.data(), sizeof(TupleRec) * nt);
     if (sh) CUDA_OK(cudaStreamWaitEvent(c->stream, c->xdone[k & 3], 0));
     CUDA_OK(cudaMemcpyAsync(dr, hr, sizeof(TupleRec) * nt, cudaMemcpyHostToDevice, c->stream));
+    // ---- contraction of batch k on the high-priority stream into cube buffer k % 2 ...
     const int buf = (int)(k & 1);
-    // per-launch events around the first batches only
-    const bool sample = sampled < 4 && k + 1 < nb;
-    const bool tr = (size_t)(4 * k + 3) < c->trace.size();
+    if (k >= 2) CUDA_OK(cudaStreamWaitEvent(c->stream, c->rdone[(k - 2) & 3], 0));  // buffer reduced
+    // per-kernel events around the first batches only: contraction [2,3], reduction [4,5]
+    const bool sample = sampled < 4;
     if (sample) CUDA_OK(cudaEventRecord(c->ev[2], c->stream));
-    if (tr) CUDA_OK(cudaEventRecord(c->trace[4 * k], c->stream));
-    if (!ct) {
-      // launch k: contraction(k) + reduction(k-1)
-      launch_contract(c, dr, nt, false, buf, &prev);
-      launch_accumulate(c, prev.ntuples, false, prev.buf, c->d_total);
-      n_contract++;
-    } else {
-      // (cT), Atrip.cxx:928-963: launch A contracts the V stores of batch k and reduces the (cT)
-      // form of batch k-1 (Tijk from its J cubes, Zijk from its V cubes); launch B contracts the J
-      // stores of batch k and reduces the plain (T) form of batch k
-      ReduceJob pct = prev;
-      pct.ct = true;
-      launch_contract(c, dr, nt, false, buf, &pct);
-      launch_accumulate(c, pct.ntuples, true, pct.buf, c->d_total + 1);
-      const ReduceJob cur{dr, nt, buf, false};
-      launch_contract(c, dr, nt, true, buf, &cur);
-      launch_accumulate(c, nt, false, buf, c->d_total);
-      n_contract += 2;
-    }
-    n_reduce += 2;
-    if (tr) CUDA_OK(cudaEventRecord(c->trace[4 * k + 1], c->stream));
+    launch_contract(c, dr, nt, false, buf);
+    n_contract++;
     if (sample) CUDA_OK(cudaEventRecord(c->ev[3], c->stream));
-    if (prev_slot >= 0) CUDA_OK(cudaEventRecord(c->rec_ev[prev_slot], c->stream));  // batch k-1 fully done
+    CUDA_OK(cudaEventRecord(c->evV[k & 3], c->stream));
+    if (ct) {
+      launch_contract(c, dr, nt, true, buf);
+      n_contract++;
+      CUDA_OK(cudaEventRecord(c->evJ[k & 3], c->stream));
+    }
     CUDA_OK(cudaEventRecord(c->cdone[k & 3], c->stream));
-    prev = ReduceJob{dr, nt, buf, false};
-    prev_slot = slot;
+    // ---- ... and its reduction on the low-priority stream: one 128-thread CTA per SM fits
+    //      beside the persistent contraction CTA of batch k+1, so it costs no time of its own
+    CUDA_OK(cudaStreamWaitEvent(c->rstream, c->evV[k & 3], 0));
+    if (sample) CUDA_OK(cudaEventRecord(c->ev[4], c->rstream));
+    launch_reduce(c, dr, nt, false, buf, c->d_total);
+    n_reduce += 2;
+    if (sample) CUDA_OK(cudaEventRecord(c->ev[5], c->rstream));
+    if (ct) {
+      CUDA_OK(cudaStreamWaitEvent(c->rstream, c->evJ[k & 3], 0));
+      launch_reduce(c, dr, nt, true, buf, c->d_total + 1);
+      n_reduce += 2;
+    }
+    CUDA_OK(cudaEventRecord(c->rdone[k & 3], c->rstream));
+    CUDA_OK(cudaEventRecord(c->rec_ev[slot], c->rstream));
     // ---- next batch: host plan (and, sharded, its exchange on the side stream)
     if (k + 1 < nb) {
       if (!sh) make_plan(k + 1);
       else if (p2p) {  // fully asynchronous: the host never waits for a transfer
         make_plan(k + 1);
-        // region (k+1) % 3 was last read by the reducers of launch k-1 (batch k-2)
-        if (k >= 1) CUDA_OK(cudaStreamWaitEvent(c->xstream, c->cdone[(k - 1) & 3], 0));
-        pull_step(c, &plans[(k + 1) % 3], (int)((k + 1) % NREGION));
+        if (k >= 1) CUDA_OK(cudaStreamWaitEvent(c->xstream, c->rdone[(k - 1) & 3], 0));  // region (k+1)%2 is free
+        pull_step(c, &plans[(k + 1) % 3], (int)((k + 1) & 1));
         CUDA_OK(cudaEventRecord(c->xdone[(k + 1) & 3], c->xstream));
       } else {
         CUDA_OK(cudaEventSynchronize(c->xdone[k & 3]));  // peers' requests for batch k+1 are on the host
         if (k + 2 < nb) make_plan(k + 2);
-        if (k >= 1) CUDA_OK(cudaStreamWaitEvent(c->xstream, c->cdone[(k - 1) & 3], 0));
+        if (k >= 1) CUDA_OK(cudaStreamWaitEvent(c->xstream, c->rdone[(k - 1) & 3], 0));  // region (k+1)%2 is free
         exchange_step(c, k + 1, &plans[(k + 1) % 3], k + 2 < nb ? &plans[(k + 2) % 3] : nullptr);
         CUDA_OK(cudaEventRecord(c->xdone[(k + 1) & 3], c->xstream));
       }
     }
     if (sample) {
-      CUDA_OK(cudaEventSynchronize(c->ev[3]));
-      float a = 0;
+      CUDA_OK(cudaEventSynchronize(c->ev[5]));
+      float a = 0, b = 0;
       CUDA_OK(cudaEventElapsedTime(&a, c->ev[2], c->ev[3]));
+      CUDA_OK(cudaEventElapsedTime(&b, c->ev[4], c->ev[5]));
       ms_contract += a;
+      ms_reduce += b;
       sampled++;
     }
   }
-  // ---- the last batch has no later launch to hide under: standalone reduction
-  if (prev.ntuples > 0) {
-    CUDA_OK(cudaEventRecord(c->ev[4], c->stream));
-    if (!ct) launch_reduce(c, prev.recs, prev.ntuples, false, prev.buf, c->d_total);
-    else launch_reduce(c, prev.recs, prev.ntuples, true, prev.buf, c->d_total + 1);
-    CUDA_OK(cudaEventRecord(c->ev[5], c->stream));
-    CUDA_OK(cudaEventRecord(c->rec_ev[prev_slot], c->stream));
-    n_reduce += 2;
-  }
+  if (nb > 0) CUDA_OK(cudaStreamWaitEvent(c->stream, c->rdone[(nb - 1) & 3], 0));  // the last reduction
   CUDA_OK(cudaEventRecord(c->ev[1], c->stream));
   double tot[2];
   CUDA_OK(cudaMemcpyAsync(tot, c->d_total, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -964,21 +935,11 @@ void run_list(atrip_b200_ctx *c, const Tuple *list, int64_t count, double *energ
   if (sh) CUDA_OK(cudaStreamSynchronize(c->xstream));
   float ms = 0;
   CUDA_OK(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]));
-  if (prev.ntuples > 0) {
-    float b = 0;
-    CUDA_OK(cudaEventElapsedTime(&b, c->ev[4], c->ev[5]));
-    ms_reduce = b;
-  }
-  for (int64_t k = 0; k < nb && (size_t)(4 * k + 3) < c->trace.size(); k++) {  // developer timeline
-    float t[2];
-    for (int q = 0; q < 2; q++) CUDA_OK(cudaEventElapsedTime(&t[q], c->ev[0], c->trace[4 * k + q]));
-    std::fprintf(stderr, "[trace] batch %3lld launch %8.3f .. %8.3f ms\n", (long long)k, t[0], t[1]);
-  }
   int64_t real = 0;
   for (int64_t t = 0; t < count; t++) real += !is_fake(list[t]);
   c->timing[0] = ms;
-  c->timing[1] = sampled ? ms_contract / sampled : 0;  // mean ms per sampled fused launch (contraction k + reduction k-1)
-  c->timing[2] = ms_reduce;                            // ms of the standalone reduction of the last batch
+  c->timing[1] = sampled ? ms_contract / sampled : 0;  // mean ms per sampled contraction launch
+  c->timing[2] = sampled ? ms_reduce / sampled : 0;    // mean ms per sampled reduction (+sum) pair
   c->timing[3] = n_contract;
   c->timing[4] = n_reduce;
   c->timing[5] = (double)real;

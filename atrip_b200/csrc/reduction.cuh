@@ -16,6 +16,7 @@
 // fixed order, so results are run-to-run deterministic and there is no per-tuple DtoH.
 #pragma once
 #include "common.cuh"
+#include "contraction.cuh"
 #include "schedule.hpp"
 
 namespace ab {
@@ -49,15 +50,10 @@ __host__ __device__ inline size_t reduce_smem_bytes(int No, bool ct) {
   return sizeof(double) * ((size_t)(ct ? 12 : 6) * RTILE + 18 * 64 + 4 * (size_t)No + 32);
 }
 
-// One (tuple, orbit split) item, evaluated by a group of NT threads (tid = 0..NT-1) that
-// synchronises with sync(): the CTA of reduce_kernel (NT = 128, __syncthreads) or the three
-// reducer warps inside contract_kernel (NT = 96, a named barrier).  sm = the group's shared memory
-// (reduce_smem_bytes).
-template <bool CT, int NT, typename Sync>
-__device__ __forceinline__ void reduce_item(const ReduceParams &P, const int tup, const int split, double *sm,
-                                            const int tid, Sync sync) {
-  constexpr int NQ = (512 + NT - 1) / NT;   // tile elements (and points) per thread
-  constexpr int NV = (18 * 64 + NT - 1) / NT;
+template <bool CT>
+__global__ void __launch_bounds__(REDUCE_THREADS, 4)
+reduce_kernel(const ReduceParams P) {
+  extern __shared__ double sm[];
   double *Wt = sm;                               // [6][RTILE]
   double *Zt = CT ? sm + 6 * RTILE : sm;         // [6][RTILE] (aliases Wt when !CT)
   double *Vb = sm + (CT ? 12 : 6) * RTILE;       // [3][6][64]
@@ -65,7 +61,10 @@ __device__ __forceinline__ void reduce_item(const ReduceParams &P, const int tup
   double *sTa = sEps + P.No, *sTb = sTa + P.No, *sTc = sTb + P.No;
   double *sRed = sTc + P.No;                     // [32]
 
+  const int tup = blockIdx.x;
   const TupleRec rec = P.recs[tup];
+  const int tid = threadIdx.x;
+  const int split = blockIdx.y;
   if (rec.fake) {  // FAKE_TUPLE contributes nothing (Atrip.cxx:629)
     if (tid == 0) P.e_tuple[(size_t)tup * P.nsplit + split] = 0.0;
     return;
@@ -80,8 +79,7 @@ __device__ __forceinline__ void reduce_item(const ReduceParams &P, const int tup
 #pragma unroll
   for (int q = 0; q < 3; q++)
     Vmat[q] = rec.vij[q] >= P.ownedV ? P.VIJc + (size_t)(rec.vij[q] - P.ownedV) * NoNo : P.VIJ + (size_t)rec.vij[q] * NoNo;
-  sync();  // the previous item's shared memory is no longer read
-  for (int i = tid; i < No; i += NT) {
+  for (int i = tid; i < No; i += REDUCE_THREADS) {
     sEps[i] = P.eps_i[i];
     sTa[i] = P.Tai[a + (size_t)i * Nv];
     sTb[i] = P.Tai[b + (size_t)i * Nv];
@@ -95,8 +93,11 @@ __device__ __forceinline__ void reduce_item(const ReduceParams &P, const int tup
   constexpr int PX[6] = {0, 0, 1, 1, 2, 2}, PY[6] = {1, 2, 0, 2, 0, 1}, PZ[6] = {2, 1, 2, 0, 1, 0};
   const int nb = (No + RT - 1) / RT;
   double esum = 0.0;
+  // element e = tid + 128 q of a tile is (x,y,z) = (l0, l1, l2 + 2 q); the same mapping gives
+  // the 4 points (il, jl, kl + 2 q) a thread evaluates
+  const int l0 = tid & 7, l1 = (tid >> 3) & 7, l2 = tid >> 6;  // l2 in 0..1
 
-  sync();  // publishes sEps, sTa, sTb, sTc
+  __syncthreads();  // publishes sEps, sTa, sTb, sTc
   int orbit = -1;
   for (int I = 0; I < nb; I++)
     for (int J = 0; J <= I; J++)
@@ -110,126 +111,112 @@ __device__ __forceinline__ void reduce_item(const ReduceParams &P, const int tup
                   c4 = (eIJ && eJK) ? 0 : (eJK ? 2 : 4), c5 = (eIJ && eJK) ? 0 : (eIJ ? 4 : (eJK ? 3 : 5));
         const int canon[6] = {0, c1, c2, c3, c4, c5};
         // ---- issue every global load of the orbit before touching shared memory: up to
-        //      6 tiles x NQ elements x 3 class cubes per thread in flight (predicated, no
-        //      branches); a tile is 512 contiguous doubles, so these are full-line coalesced loads
-        double lk[6][NQ], lj[6][NQ], li[6][NQ];
+        //      6 tiles x 4 elements x 3 class cubes per thread in flight (predicated, no branches);
+        //      a tile is 512 contiguous doubles, so these are full-line coalesced loads
+        double lk[6][4], lj[6][4], li[6][4];
 #pragma unroll
         for (int p = 0; p < 6; p++) {
-          const bool okp = canon[p] == p;
-          const size_t tb = okp ? (((size_t)blk[PZ[p]] * nb + blk[PY[p]]) * nb + blk[PX[p]]) * 512 + tid : 0;
+          const bool ok = canon[p] == p;
+          const size_t tb = ok ? (((size_t)blk[PZ[p]] * nb + blk[PY[p]]) * nb + blk[PX[p]]) * 512 + tid : 0;
 #pragma unroll
-          for (int q = 0; q < NQ; q++) {
-            const bool ok = okp && (512 % NT == 0 || tid + NT * q < 512);
-            lk[p][q] = ok ? Ck[tb + NT * q] : 0.0;
-            lj[p][q] = ok ? Cj[tb + NT * q] : 0.0;
-            li[p][q] = ok ? Ci[tb + NT * q] : 0.0;
+          for (int q = 0; q < 4; q++) {
+            lk[p][q] = ok ? Ck[tb + 128 * q] : 0.0;
+            lj[p][q] = ok ? Cj[tb + 128 * q] : 0.0;
+            li[p][q] = ok ? Ci[tb + 128 * q] : 0.0;
           }
         }
         // Vabij blocks: Vb[mat][pair(X,Y)][xl + 8 yl] = Vmat[x + y No]
-        double lv[NV];
+        double lv[9];
 #pragma unroll
-        for (int q = 0; q < NV; q++) {
-          const int e = tid + NT * q;
+        for (int q = 0; q < 9; q++) {
+          const int e = tid + REDUCE_THREADS * q;  // < 18 * 64 = 9 * 128
           const int mat = e / 384, r = e - mat * 384, pr = r >> 6, xl = r & 7, yl = (r >> 3) & 7;
           const int X = pr >> 1, Y = (pr & 1) ? (X == 2 ? 1 : 2) : (X == 0 ? 1 : 0);
           const int x = blk[X] * RT + xl, y = blk[Y] * RT + yl;
-          lv[q] = (e < 18 * 64 && x < No && y < No) ? Vmat[mat < 3 ? mat : 0][x + (size_t)y * No] : 0.0;
+          lv[q] = (x < No && y < No) ? Vmat[mat][x + (size_t)y * No] : 0.0;
         }
-        sync();  // previous orbit fully consumed
+        __syncthreads();  // previous orbit fully consumed
 #pragma unroll
         for (int p = 0; p < 6; p++)
           if (canon[p] == p) {
 #pragma unroll
-            for (int q = 0; q < NQ; q++) {
-              const int e = tid + NT * q;
-              if (512 % NT == 0 || e < 512)
-                Wt[p * RTILE + tile_pos(e & 7, (e >> 3) & 7, e >> 6)] = (lk[p][q] + lj[p][q]) + li[p][q];
-            }
+            for (int q = 0; q < 4; q++) Wt[p * RTILE + tile_pos(l0, l1, l2 + 2 * q)] = (lk[p][q] + lj[p][q]) + li[p][q];
           }
 #pragma unroll
-        for (int q = 0; q < NV; q++)
-          if ((18 * 64) % NT == 0 || tid + NT * q < 18 * 64) Vb[tid + NT * q] = lv[q];
+        for (int q = 0; q < 9; q++) Vb[tid + REDUCE_THREADS * q] = lv[q];
         if (CT) {  // (cT): Zijk comes from the V-pass cubes, Tijk (above) from the J pass
 #pragma unroll
           for (int p = 0; p < 6; p++)
             if (canon[p] == p) {
-              const size_t tb = (((size_t)blk[PZ[p]] * nb + blk[PY[p]]) * nb + blk[PX[p]]) * 512;
+              const size_t tb = (((size_t)blk[PZ[p]] * nb + blk[PY[p]]) * nb + blk[PX[p]]) * 512 + tid;
 #pragma unroll
-              for (int q = 0; q < NQ; q++) {
-                const int e = tid + NT * q;
-                if (512 % NT == 0 || e < 512)
-                  Zt[p * RTILE + tile_pos(e & 7, (e >> 3) & 7, e >> 6)] = (Zk[tb + e] + Zj[tb + e]) + Zi[tb + e];
-              }
+              for (int q = 0; q < 4; q++)
+                Zt[p * RTILE + tile_pos(l0, l1, l2 + 2 * q)] = (Zk[tb + 128 * q] + Zj[tb + 128 * q]) + Zi[tb + 128 * q];
             }
         }
-        sync();
+        __syncthreads();
         // ---- energy of the (i in I, j in J, k in K) points with k <= j <= i
-        const double *Vbc = Vb, *Vac = Vb + 384, *Vab = Vb + 768;
+        const int il = l0, jl = l1;
+        const int i = I * RT + il, j = J * RT + jl;
+        if (i < No && j <= i) {
+          const double *Vbc = Vb, *Vac = Vb + 384, *Vab = Vb + 768;
+          // Vabij pair blocks: 0 (I,J) 1 (I,K) 2 (J,I) 3 (J,K) 4 (K,I) 5 (K,J)
+          const int pij = 0 * 64 + il + 8 * jl, pji = 2 * 64 + jl + 8 * il;
+          const double tai = sTa[i], taj = sTa[j], tbi = sTb[i], tbj = sTb[j], tci = sTc[i], tcj = sTc[j];
+          const double eij = sEps[i] + sEps[j];
+          const double facij = (i == j) ? 0.5 : 1.0;
 #pragma unroll
-        for (int q = 0; q < NQ; q++) {
-          const int e = tid + NT * q;
-          const int il = e & 7, jl = (e >> 3) & 7, kl = e >> 6;
-          const int i = I * RT + il, j = J * RT + jl, k = K * RT + kl;
-          if ((512 % NT == 0 || e < 512) && i < No && j <= i && k <= j) {
-            // tiles: 0 (I,J,K) 1 (I,K,J) 2 (J,I,K) 3 (J,K,I) 4 (K,I,J) 5 (K,J,I)
-            const int o0 = tile_pos(il, jl, kl), o1 = RTILE * c1 + tile_pos(il, kl, jl);
-            const int o2 = RTILE * c2 + tile_pos(jl, il, kl), o3 = RTILE * c3 + tile_pos(jl, kl, il);
-            const int o4 = RTILE * c4 + tile_pos(kl, il, jl), o5 = RTILE * c5 + tile_pos(kl, jl, il);
-            const double A = Wt[o0], B = Wt[o1], C = Wt[o2], D = Wt[o3], E = Wt[o4], F = Wt[o5];
-            // Vabij pair blocks: 0 (I,J) 1 (I,K) 2 (J,I) 3 (J,K) 4 (K,I) 5 (K,J)
-            const int pij = 0 * 64 + il + 8 * jl, pik = 1 * 64 + il + 8 * kl, pji = 2 * 64 + jl + 8 * il;
-            const int pjk = 3 * 64 + jl + 8 * kl, pki = 4 * 64 + kl + 8 * il, pkj = 5 * 64 + kl + 8 * jl;
-            const double tai = sTa[i], taj = sTa[j], tak = sTa[k];
-            const double tbi = sTb[i], tbj = sTb[j], tbk = sTb[k];
-            const double tci = sTc[i], tcj = sTc[j], tck = sTc[k];
-            // Z[x,y,z] = T[x,y,z] + Tai[a,x] Vbc[y,z] + Tai[b,y] Vac[x,z] + Tai[c,z] Vab[x,y]
-            // (Equations.cxx:420-422, three separate += in this order)
-            double U = Zt[o0], V = Zt[o1], W = Zt[o2], X = Zt[o3], Y = Zt[o4], Z = Zt[o5];
-            U = ((U + tai * Vbc[pjk]) + tbj * Vac[pik]) + tck * Vab[pij];  // Z[i,j,k]
-            V = ((V + tai * Vbc[pkj]) + tbk * Vac[pij]) + tcj * Vab[pik];  // Z[i,k,j]
-            W = ((W + taj * Vbc[pik]) + tbi * Vac[pjk]) + tck * Vab[pji];  // Z[j,i,k]
-            X = ((X + taj * Vbc[pki]) + tbk * Vac[pji]) + tci * Vab[pjk];  // Z[j,k,i]
-            Y = ((Y + tak * Vbc[pij]) + tbi * Vac[pkj]) + tcj * Vab[pki];  // Z[k,i,j]
-            Z = ((Z + tak * Vbc[pji]) + tbj * Vac[pki]) + tci * Vab[pkj];  // Z[k,j,i]
-            const double facjk = (j == k) ? 0.5 : 1.0, facij = (i == j) ? 0.5 : 1.0;
-            const double den = epsabc - ((sEps[i] + sEps[j]) + sEps[k]);
-            double value;
-            if (!same) {  // get_energy_distinct, Equations.cxx:129-166
-              const double UXY = U + (X + Y), VWZ = V + (W + Z);
-              const double ADE = A + (D + E), BCF = B + (C + F);
-              const double first = A * U + (B * V + (C * W + (D * X + (E * Y + F * Z))));
-              const double second = (UXY - 2.0 * VWZ) * ADE;
-              const double third = (VWZ - 2.0 * UXY) * BCF;
-              value = 3.0 * first + (second + third);
-            } else {  // get_energy_same, Equations.cxx:209-226: cyclic permutations only
-              const double ABC = A + (D + E), UVW = U + (X + Y);
-              value = 3.0 * ((A * U + D * X) + E * Y) - ABC * UVW;
+          for (int q = 0; q < 4; q++) {
+            const int kl = l2 + 2 * q, k = K * RT + kl;
+            if (k <= j) {
+              // tiles: 0 (I,J,K) 1 (I,K,J) 2 (J,I,K) 3 (J,K,I) 4 (K,I,J) 5 (K,J,I)
+              const int o0 = tile_pos(il, jl, kl), o1 = RTILE * c1 + tile_pos(il, kl, jl);
+              const int o2 = RTILE * c2 + tile_pos(jl, il, kl), o3 = RTILE * c3 + tile_pos(jl, kl, il);
+              const int o4 = RTILE * c4 + tile_pos(kl, il, jl), o5 = RTILE * c5 + tile_pos(kl, jl, il);
+              const double A = Wt[o0], B = Wt[o1], C = Wt[o2], D = Wt[o3], E = Wt[o4], F = Wt[o5];
+              const int pik = 1 * 64 + il + 8 * kl, pjk = 3 * 64 + jl + 8 * kl;
+              const int pki = 4 * 64 + kl + 8 * il, pkj = 5 * 64 + kl + 8 * jl;
+              const double tak = sTa[k], tbk = sTb[k], tck = sTc[k];
+              // Z[x,y,z] = T[x,y,z] + Tai[a,x] Vbc[y,z] + Tai[b,y] Vac[x,z] + Tai[c,z] Vab[x,y]
+              // (Equations.cxx:420-422, three separate += in this order)
+              double U = Zt[o0], V = Zt[o1], W = Zt[o2], X = Zt[o3], Y = Zt[o4], Z = Zt[o5];
+              U = ((U + tai * Vbc[pjk]) + tbj * Vac[pik]) + tck * Vab[pij];  // Z[i,j,k]
+              V = ((V + tai * Vbc[pkj]) + tbk * Vac[pij]) + tcj * Vab[pik];  // Z[i,k,j]
+              W = ((W + taj * Vbc[pik]) + tbi * Vac[pjk]) + tck * Vab[pji];  // Z[j,i,k]
+              X = ((X + taj * Vbc[pki]) + tbk * Vac[pji]) + tci * Vab[pjk];  // Z[j,k,i]
+              Y = ((Y + tak * Vbc[pij]) + tbi * Vac[pkj]) + tcj * Vab[pki];  // Z[k,i,j]
+              Z = ((Z + tak * Vbc[pji]) + tbj * Vac[pki]) + tci * Vab[pkj];  // Z[k,j,i]
+              const double facjk = (j == k) ? 0.5 : 1.0;
+              const double den = epsabc - (eij + sEps[k]);
+              double value;
+              if (!same) {  // get_energy_distinct, Equations.cxx:129-166
+                const double UXY = U + (X + Y), VWZ = V + (W + Z);
+                const double ADE = A + (D + E), BCF = B + (C + F);
+                const double first = A * U + (B * V + (C * W + (D * X + (E * Y + F * Z))));
+                const double second = (UXY - 2.0 * VWZ) * ADE;
+                const double third = (VWZ - 2.0 * UXY) * BCF;
+                value = 3.0 * first + (second + third);
+              } else {  // get_energy_same, Equations.cxx:209-226: cyclic permutations only
+                const double ABC = A + (D + E), UVW = U + (X + Y);
+                value = 3.0 * ((A * U + D * X) + E * Y) - ABC * UVW;
+              }
+              esum += ((2.0 * value) / den) * (facjk * facij);
             }
-            esum += ((2.0 * value) / den) * (facjk * facij);
           }
         }
       }
 
-  // group reduction in a fixed order
+  // block reduction in a fixed order
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) esum += __shfl_down_sync(0xffffffffu, esum, off);
-  sync();
+  __syncthreads();
   if ((tid & 31) == 0) sRed[tid >> 5] = esum;
-  sync();
+  __syncthreads();
   if (tid == 0) {
     double s = 0.0;
-    for (int w = 0; w < NT / 32; w++) s += sRed[w];
+    for (int w = 0; w < REDUCE_THREADS / 32; w++) s += sRed[w];
     P.e_tuple[(size_t)tup * P.nsplit + split] = s;
   }
-}
-
-// standalone form: one CTA per (tuple, orbit split); used for the last batch of a run (every
-// other batch is reduced by the reducer warps of the next contraction launch)
-template <bool CT>
-__global__ void __launch_bounds__(REDUCE_THREADS, 4)
-reduce_kernel(const ReduceParams P) {
-  extern __shared__ double sm[];
-  reduce_item<CT, REDUCE_THREADS>(P, blockIdx.x, blockIdx.y, sm, threadIdx.x, [] { __syncthreads(); });
 }
 
 // total[0] += sum_t e_tuple[t] in a fixed order (one CTA); keeps the energy on the device
