@@ -448,20 +448,13 @@ void create_impl(atrip_b200_ctx *c) {
   for (auto &ev : c->evJ) CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   for (auto &ev : c->rdone) CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
 
-  // one reduction CTA (128 threads, <= 128 registers) must fit on an SM beside the contraction CTA
-  // so the reduction of batch k hides under the contraction of batch k+1: leave it its shared memory
-  const size_t reduce_room = reduce_smem_bytes(c->No, cfg.with_J != 0) + 2048;
-  c->plan = plan_contraction(c->No, c->smem_limit - reduce_room);
+  c->plan = plan_contraction(c->No, c->smem_limit);
   REQUIRE(c->plan.k, "no contraction kernel variant fits this No");
   CUDA_OK(cudaFuncSetAttribute(contract_fn(c), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->plan.smem));
   CUDA_OK(cudaFuncSetAttribute((const void *)reduce_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)reduce_smem_bytes(c->No, false)));
   CUDA_OK(cudaFuncSetAttribute((const void *)reduce_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)reduce_smem_bytes(c->No, true)));
-  // both kernels ask for the largest shared-memory carve-out, otherwise an SM configured for the
-  // contraction alone has no room left for the reduction CTA that should run beside it
-  for (const void *fn : {contract_fn(c), (const void *)reduce_kernel<false>, (const void *)reduce_kernel<true>})
-    CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
 
   // ---- which slices live here: everything (replica) or the slices this rank owns
   const int sn = (cfg.resident || cfg.nranks == 1) ? 1 : cfg.nranks;
@@ -872,6 +865,9 @@ void run_list(atrip_b200_ctx *c, const Tuple *list, int64_t count, double *energ
     if (sh) CUDA_OK(cudaStreamWaitEvent(c->stream, c->xdone[k & 3], 0));
     CUDA_OK(cudaMemcpyAsync(dr, hr, sizeof(TupleRec) * nt, cudaMemcpyHostToDevice, c->stream));
     // ---- contraction of batch k on the high-priority stream into cube buffer k % 2 ...
+    //      (the two kernels cannot share an SM profitably: plain FP64 instructions and DMMA use
+    //      the same datapath, profiles/r01_fused_reducers_rejected_ncu.txt; the second stream only
+    //      lets the reduction fill the ragged tail of the next contraction launch)
     const int buf = (int)(k & 1);
     if (k >= 2) CUDA_OK(cudaStreamWaitEvent(c->stream, c->rdone[(k - 2) & 3], 0));  // buffer reduced
     // per-kernel events around the first batches only: contraction [2,3], reduction [4,5]
@@ -887,8 +883,7 @@ void run_list(atrip_b200_ctx *c, const Tuple *list, int64_t count, double *energ
       CUDA_OK(cudaEventRecord(c->evJ[k & 3], c->stream));
     }
     CUDA_OK(cudaEventRecord(c->cdone[k & 3], c->stream));
-    // ---- ... and its reduction on the low-priority stream: one 128-thread CTA per SM fits
-    //      beside the persistent contraction CTA of batch k+1, so it costs no time of its own
+    // ---- ... and its reduction on the low-priority stream
     CUDA_OK(cudaStreamWaitEvent(c->rstream, c->evV[k & 3], 0));
     if (sample) CUDA_OK(cudaEventRecord(c->ev[4], c->rstream));
     launch_reduce(c, dr, nt, false, buf, c->d_total);

@@ -15,6 +15,8 @@
 // with warp shuffles to one double per tuple.  The batch sum is a second, single-CTA kernel in a
 // fixed order, so results are run-to-run deterministic and there is no per-tuple DtoH.
 #pragma once
+#include <utility>
+
 #include "common.cuh"
 #include "contraction.cuh"
 #include "schedule.hpp"
@@ -50,8 +52,31 @@ __host__ __device__ inline size_t reduce_smem_bytes(int No, bool ct) {
   return sizeof(double) * ((size_t)(ct ? 12 : 6) * RTILE + 18 * 64 + 4 * (size_t)No + 32);
 }
 
+// compile-time loop over the six permuted tiles: body(std::integral_constant<int, p>) with
+// p = 0 (I,J,K) 1 (I,K,J) 2 (J,I,K) 3 (J,K,I) 4 (K,I,J) 5 (K,J,I).  Everything that depends on p
+// is a constant in each instantiation, so the staging arrays stay in registers (with a run-time p
+// nvcc indexed the tables through selects and demoted every array to local memory).
+template <int P>
+struct TilePerm {
+  static constexpr int X = P >> 1;
+  static constexpr int Y = (P == 0 || P == 5) ? 1 : ((P == 1 || P == 3) ? 2 : 0);
+  static constexpr int Z = 3 - X - Y;
+};
+__device__ __forceinline__ int pick3(int which, int I, int J, int K) { return which == 0 ? I : (which == 1 ? J : K); }
+template <typename F, int... Ps>
+__device__ __forceinline__ void for_tiles_impl(F &&f, std::integer_sequence<int, Ps...>) {
+  (f(std::integral_constant<int, Ps>{}), ...);
+}
+template <typename F>
+__device__ __forceinline__ void for_tiles(F &&f) {
+  for_tiles_impl(f, std::make_integer_sequence<int, 6>{});
+}
+
+#ifndef REDUCE_MINBLOCKS
+#define REDUCE_MINBLOCKS 4
+#endif
 template <bool CT>
-__global__ void __launch_bounds__(REDUCE_THREADS, 4)
+__global__ void __launch_bounds__(REDUCE_THREADS, REDUCE_MINBLOCKS)
 reduce_kernel(const ReduceParams P) {
   extern __shared__ double sm[];
   double *Wt = sm;                               // [6][RTILE]
@@ -88,9 +113,6 @@ reduce_kernel(const ReduceParams P) {
   const double epsabc = P.eps_a[a] + P.eps_a[b] + P.eps_a[c];  // Atrip.cxx:643-646
   const bool same = (a == b) != (b == c);                     // Atrip.cxx:640-650
 
-  // block coordinates of permuted tile p = (blk[PX], blk[PY], blk[PZ]):
-  // 0 (I,J,K) 1 (I,K,J) 2 (J,I,K) 3 (J,K,I) 4 (K,I,J) 5 (K,J,I)
-  constexpr int PX[6] = {0, 0, 1, 1, 2, 2}, PY[6] = {1, 2, 0, 2, 0, 1}, PZ[6] = {2, 1, 2, 0, 1, 0};
   const int nb = (No + RT - 1) / RT;
   double esum = 0.0;
   // element e = tid + 128 q of a tile is (x,y,z) = (l0, l1, l2 + 2 q); the same mapping gives
@@ -103,56 +125,64 @@ reduce_kernel(const ReduceParams P) {
     for (int J = 0; J <= I; J++)
       for (int K = 0; K <= J; K++) {
         if (++orbit % P.nsplit != split) continue;
-        const int blk[3] = {I, J, K};
         // coincident block coordinates give identical tiles: build each distinct one once
-        // (tile p -> canon[p])
+        // (tile p -> its first equal tile c_p)
         const bool eIJ = (I == J), eJK = (J == K);
         const int c1 = eJK ? 0 : 1, c2 = eIJ ? 0 : 2, c3 = (eIJ && eJK) ? 0 : (eIJ ? 1 : 3),
                   c4 = (eIJ && eJK) ? 0 : (eJK ? 2 : 4), c5 = (eIJ && eJK) ? 0 : (eIJ ? 4 : (eJK ? 3 : 5));
-        const int canon[6] = {0, c1, c2, c3, c4, c5};
+        const bool d1 = c1 == 1, d2 = c2 == 2, d3 = c3 == 3, d4 = c4 == 4, d5 = c5 == 5;
+        auto distinct = [&](int p) { return p == 0 || (p == 1 ? d1 : (p == 2 ? d2 : (p == 3 ? d3 : (p == 4 ? d4 : d5)))); };
         // ---- issue every global load of the orbit before touching shared memory: up to
         //      6 tiles x 4 elements x 3 class cubes per thread in flight (predicated, no branches);
         //      a tile is 512 contiguous doubles, so these are full-line coalesced loads
         double lk[6][4], lj[6][4], li[6][4];
-#pragma unroll
-        for (int p = 0; p < 6; p++) {
-          const bool ok = canon[p] == p;
-          const size_t tb = ok ? (((size_t)blk[PZ[p]] * nb + blk[PY[p]]) * nb + blk[PX[p]]) * 512 + tid : 0;
+        for_tiles([&](auto pc) {
+          constexpr int p = decltype(pc)::value;
+          using T = TilePerm<p>;
+          const bool ok = distinct(p);
+          const size_t tb =
+              (((size_t)pick3(T::Z, I, J, K) * nb + pick3(T::Y, I, J, K)) * nb + pick3(T::X, I, J, K)) * 512 + tid;
 #pragma unroll
           for (int q = 0; q < 4; q++) {
             lk[p][q] = ok ? Ck[tb + 128 * q] : 0.0;
             lj[p][q] = ok ? Cj[tb + 128 * q] : 0.0;
             li[p][q] = ok ? Ci[tb + 128 * q] : 0.0;
           }
-        }
-        // Vabij blocks: Vb[mat][pair(X,Y)][xl + 8 yl] = Vmat[x + y No]
+        });
+        // Vabij blocks: Vb[mat][pair(X,Y)][xl + 8 yl] = Vmat[x + y No]; pair blocks
+        // 0 (I,J) 1 (I,K) 2 (J,I) 3 (J,K) 4 (K,I) 5 (K,J)
         double lv[9];
 #pragma unroll
         for (int q = 0; q < 9; q++) {
           const int e = tid + REDUCE_THREADS * q;  // < 18 * 64 = 9 * 128
           const int mat = e / 384, r = e - mat * 384, pr = r >> 6, xl = r & 7, yl = (r >> 3) & 7;
           const int X = pr >> 1, Y = (pr & 1) ? (X == 2 ? 1 : 2) : (X == 0 ? 1 : 0);
-          const int x = blk[X] * RT + xl, y = blk[Y] * RT + yl;
-          lv[q] = (x < No && y < No) ? Vmat[mat][x + (size_t)y * No] : 0.0;
+          const int x = pick3(X, I, J, K) * RT + xl, y = pick3(Y, I, J, K) * RT + yl;
+          const double *vm = mat == 0 ? Vmat[0] : (mat == 1 ? Vmat[1] : Vmat[2]);
+          lv[q] = (x < No && y < No) ? vm[x + (size_t)y * No] : 0.0;
         }
         __syncthreads();  // previous orbit fully consumed
-#pragma unroll
-        for (int p = 0; p < 6; p++)
-          if (canon[p] == p) {
+        for_tiles([&](auto pc) {
+          constexpr int p = decltype(pc)::value;
+          if (distinct(p)) {
 #pragma unroll
             for (int q = 0; q < 4; q++) Wt[p * RTILE + tile_pos(l0, l1, l2 + 2 * q)] = (lk[p][q] + lj[p][q]) + li[p][q];
           }
+        });
 #pragma unroll
         for (int q = 0; q < 9; q++) Vb[tid + REDUCE_THREADS * q] = lv[q];
         if (CT) {  // (cT): Zijk comes from the V-pass cubes, Tijk (above) from the J pass
-#pragma unroll
-          for (int p = 0; p < 6; p++)
-            if (canon[p] == p) {
-              const size_t tb = (((size_t)blk[PZ[p]] * nb + blk[PY[p]]) * nb + blk[PX[p]]) * 512 + tid;
+          for_tiles([&](auto pc) {
+            constexpr int p = decltype(pc)::value;
+            using T = TilePerm<p>;
+            if (distinct(p)) {
+              const size_t tb =
+                  (((size_t)pick3(T::Z, I, J, K) * nb + pick3(T::Y, I, J, K)) * nb + pick3(T::X, I, J, K)) * 512 + tid;
 #pragma unroll
               for (int q = 0; q < 4; q++)
                 Zt[p * RTILE + tile_pos(l0, l1, l2 + 2 * q)] = (Zk[tb + 128 * q] + Zj[tb + 128 * q]) + Zi[tb + 128 * q];
             }
+          });
         }
         __syncthreads();
         // ---- energy of the (i in I, j in J, k in K) points with k <= j <= i
