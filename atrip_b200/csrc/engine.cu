@@ -568,6 +568,13 @@ void destroy_impl(atrip_b200_ctx *c) {
   cudaSetDevice(c->cfg.device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->xstream) cudaStreamSynchronize(c->xstream);
+  // P2P transport: a peer may still be pulling slices out of this rank's stores -- destroying a
+  // sharded context is collective (like MPI_Finalize): wait until every rank got here
+  if (c->comm && nccl().ok && c->transport == 2 && c->d_reduce && c->stream) {
+    if (cudaMemsetAsync(c->d_reduce, 0, sizeof(double), c->stream) == cudaSuccess &&
+        nccl().AllReduce(c->d_reduce, c->d_reduce, 1, ncclFloat64, ncclSum, c->comm, c->stream) == ncclSuccess)
+      cudaStreamSynchronize(c->stream);
+  }
   for (auto &v : c->peer)
     for (size_t p = 0; p < v.size(); p++)
       if (v[p] && (int)p != c->cfg.rank) cudaIpcCloseMemHandle(v[p]);

@@ -37,6 +37,13 @@ CONFIGS = {  # BASELINE.json configs; scale keeps |E| = O(1e-2..1) for the parit
     "c1": dict(No=10, Nv=40, scale=0.01, tuples_per_step=11440, desc="No=10 Nv=40 (CPU-runnable case)"),
     "c2": dict(No=40, Nv=400, scale=0.001, tuples_per_step=196608, desc="No=40 Nv=400 FP64 random tensors"),
     "c5s": dict(No=32, Nv=480, scale=0.001, tuples_per_step=98304, desc="No=32 high Nv/No (c5 scaled to 1 GPU)"),
+    # multi-GPU configs (sharded stores); host tensors of these sizes do not exist anywhere, so no e2e leg
+    "c3": dict(No=64, Nv=640, scale=0.0005, tuples_per_step=16900, no_e2e=True,
+               desc="No=64 Nv=640 FP64 random tensors (170 GB of stores)"),
+    "c4": dict(No=100, Nv=1000, scale=0.0002, tuples_per_step=3900, no_e2e=True, min_gpus=8,
+               desc="No=100 Nv=1000 FP64 random tensors (1.0 TB of stores over 8 GPUs)"),
+    "c5": dict(No=32, Nv=1200, scale=0.0005, tuples_per_step=59200, no_e2e=True, min_gpus=4,
+               desc="No=32 Nv=1200 FP64 random tensors, high Nv/No (0.5 TB of stores)"),
 }
 SEED = 12345
 
@@ -207,6 +214,10 @@ def main():
     cfg = dict(CONFIGS[args.config], name=args.config)
     if args.tuples_per_step:
         cfg["tuples_per_step"] = args.tuples_per_step
+    if cfg.get("no_e2e"):
+        args.no_e2e = True
+    assert args.impl == "reference" or args.gpus >= cfg.get("min_gpus", 1), \
+        f"{args.config} needs at least {cfg.get('min_gpus')} GPUs (stores are sharded over the ranks)"
     if args.impl == "reference":
         return run_reference_arm(args, cfg)
 

@@ -45,6 +45,8 @@ typedef struct atrip_b200_config {
 
 /* ---- lifecycle (replaces the ACC set-up in Atrip::run, Atrip.cxx:78-171, 217-218, 364-380) */
 int atrip_b200_create(atrip_b200_ctx **ctx, const atrip_b200_config *cfg);
+/* with sharded stores and transport 2, destroy is collective: it waits until every rank has
+ * called it, because a peer may still be reading this rank's stores */
 int atrip_b200_destroy(atrip_b200_ctx *ctx);
 const char *atrip_b200_last_error(void);
 const char *atrip_b200_version(void);

@@ -107,3 +107,64 @@ def test_sharded_ingest_and_tuple_debug_match_oracle(oracle, transport):
             assert abs(ge - oe) <= E_REL * abs(oe), abc
             assert np.abs(T - oT).max() <= CUBE_REL * np.abs(oT).max(), abc
             assert np.abs(Z - oZ).max() <= CUBE_REL * np.abs(oZ).max(), abc
+
+
+def _big_worker(rank, world, q_id, q_out, No, Nv, seed, scale, tuples):
+    sys.path.insert(0, ROOT)
+    import atrip_b200
+    from atrip_b200 import capi
+    eng = atrip_b200.Engine(No, Nv, device=rank, rank=rank, nranks=world, resident=False)
+    if rank == 0:
+        uid = capi.comm_unique_id()
+        for _ in range(world - 1):
+            q_id.put(uid)
+    else:
+        uid = q_id.get(timeout=300)
+    eng.comm_init(uid)
+    eng.fill_synthetic(seed, scale)
+    out = [eng.tuple_debug(*abc, cubes=False)[0] for abc in tuples]  # remote slices pulled from the owners
+    q_out.put((rank, out))
+    eng.close()  # collective: waits for the peers that may still read this rank's stores
+
+
+def test_c4_tuples_on_8_gpus_match_reference_functions(oracle):
+    """BASELINE config 4 (No=100, Nv=1000, 1 TB of stores over 8 GPUs): tuple energies from the
+    sharded engine against the reference's doubles/singles/energy functions evaluated on the
+    same synthetic slices (generated slice by slice on the host, no full tensors)"""
+    import torch
+    import torch.multiprocessing as mp
+    from oracle.oracle import EPS_A, EPS_I, TAI, Reference
+    if torch.cuda.device_count() < 8:
+        pytest.skip("needs 8 GPUs")
+    No, Nv, seed, scale, world = 100, 1000, 12345, 0.0002, 8
+    tuples = [(3, 500, 997), (17, 17, 640), (250, 251, 252)]
+    ctx = mp.get_context("spawn")
+    q_id, q_out = ctx.Queue(), ctx.Queue()
+    procs = [ctx.Process(target=_big_worker, args=(r, world, q_id, q_out, No, Nv, seed, scale, tuples)) for r in range(world)]
+    for p in procs:
+        p.start()
+    # meanwhile: the same tuples on the host
+    ref = Reference() if Reference.available() else None
+    epsi, epsa = oracle.fill(seed, EPS_I, scale, No), oracle.fill(seed, EPS_A, scale, Nv)
+    tai = oracle.fill(seed, TAI, scale, No * Nv)
+    want = []
+    for abc in tuples:
+        S = oracle.synth_tuple_slices(No, Nv, abc, seed=seed, scale=scale)
+        f = ref if ref is not None else oracle
+        T = f.doubles(No, Nv, S, (np.empty(No ** 3), np.empty(No ** 3))) if ref is not None else f.doubles(No, Nv, S)
+        Z = f.singles(No, Nv, abc, tai, S, T)
+        eps = float(epsa[abc[0]] + epsa[abc[1]] + epsa[abc[2]])
+        same = (abc[0] == abc[1]) != (abc[1] == abc[2])
+        want.append((f.energy_same if same else f.energy_distinct)(eps, No, epsi, T, Z))
+    try:
+        res = [q_out.get(timeout=900) for _ in range(world)]
+        for p in procs:
+            p.join(timeout=120)
+            assert p.exitcode == 0
+    finally:
+        for p in procs:
+            if p.is_alive():
+                p.kill()
+    for rank, got in res:
+        for abc, g, w in zip(tuples, got, want):
+            assert abs(g - w) <= E_REL * abs(w), (rank, abc, g, w)
