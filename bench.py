@@ -314,6 +314,16 @@ def main():
     # ------------------------------------------------ e2e: host tensors through the C-ABI
     e2e = None
     if not args.no_e2e:
+        # every rank pins its own copy of the host tensors: make sure the box has the memory
+        need = 8 * (2 * Nv * Nv * No * No + No ** 3 * Nv + Nv ** 3 * No) * world
+        try:
+            import psutil
+            if psutil.virtual_memory().available < 1.25 * need:
+                args.no_e2e = True
+                e2e = {"skipped": f"host memory: {need / 1e9:.0f} GB of pinned tensors needed for {world} ranks"}
+        except ImportError:
+            pass
+    if not args.no_e2e:
         host = host_tensors(cfg, local)
         h2d = sum(t.numel() * 8 for t in host.values())
 
