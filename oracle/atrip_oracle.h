@@ -77,6 +77,34 @@ int oracle_run(long No, long Nv, const double *epsi, const double *epsa,
                const double *Jabci, const uint64_t *tuples, long n_tuples,
                double *energy, double *ct_energy);
 
+/* ---- F = std::complex<double> (atrip_oracle_z.c); arrays are interleaved (re, im) */
+void oracle_fill_z(uint64_t seed, int tensor_id, double scale, uint64_t first,
+                   uint64_t count, double *out);
+void oracle_doubles_z(long No, long Nv, const double *VAB, const double *VAC,
+                      const double *VBC, const double *VBA, const double *VCA,
+                      const double *VCB, const double *HA, const double *HB,
+                      const double *HC, const double *TA, const double *TB,
+                      const double *TC, const double *TAB, const double *TAC,
+                      const double *TBC, double *Tijk);
+void oracle_singles_z(long No, long Nv, long a, long b, long c, const double *Tph,
+                      const double *VABij, const double *VACij,
+                      const double *VBCij, double *Zijk);
+double oracle_energy_distinct_z(double epsabc, long No, const double *epsi,
+                                const double *Tijk, const double *Zijk);
+double oracle_energy_same_z(double epsabc, long No, const double *epsi,
+                            const double *Tijk, const double *Zijk);
+double oracle_tuple_energy_z(long No, long Nv, const double *epsi, const double *epsa,
+                             const double *Tai, const double *Tabij,
+                             const double *Vabij, const double *Vijka,
+                             const double *Vabci, const double *Jijka,
+                             const double *Jabci, long a, long b, long c,
+                             double *Tijk_out, double *Zijk_out, double *ct);
+int oracle_run_z(long No, long Nv, const double *epsi, const double *epsa,
+                 const double *Tai, const double *Tabij, const double *Vabij,
+                 const double *Vijka, const double *Vabci, const double *Jijka,
+                 const double *Jabci, const uint64_t *tuples, long n_tuples,
+                 double *energy, double *ct_energy);
+
 #ifdef __cplusplus
 }
 #endif

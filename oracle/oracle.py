@@ -72,6 +72,16 @@ class Oracle:
         L.oracle_owner_pair.restype = C.c_long
         L.oracle_owner_pair.argtypes = [C.c_long] * 4
         L.oracle_run.argtypes = [C.c_long, C.c_long] + [_dp] * 9 + [_up, C.c_long, _dp, _dp]
+        # F = Complex (atrip_oracle_z.c): complex128 arrays passed as interleaved doubles
+        L.oracle_fill_z.argtypes = [C.c_uint64, C.c_int, C.c_double, C.c_uint64, C.c_uint64, _dp]
+        L.oracle_doubles_z.argtypes = [C.c_long, C.c_long] + [_dp] * 16
+        L.oracle_singles_z.argtypes = [C.c_long] * 5 + [_dp] * 5
+        for f in (L.oracle_energy_distinct_z, L.oracle_energy_same_z):
+            f.restype = C.c_double
+            f.argtypes = [C.c_double, C.c_long, _dp, _dp, _dp]
+        L.oracle_tuple_energy_z.restype = C.c_double
+        L.oracle_tuple_energy_z.argtypes = [C.c_long, C.c_long] + [_dp] * 9 + [C.c_long] * 3 + [_dp] * 3
+        L.oracle_run_z.argtypes = [C.c_long, C.c_long] + [_dp] * 9 + [_up, C.c_long, _dp, _dp]
 
     # ---- inputs
     def fill(self, seed, tensor_id, scale, count, first=0):
@@ -84,6 +94,77 @@ class Oracle:
         ids = [EPS_I, EPS_A, TAI, TABIJ, VABIJ, VIJKA, VABCI] + ([JIJKA, JABCI] if with_J else [])
         sz = tensor_sizes(No, Nv)
         return {t: self.fill(seed, t, scale, sz[t]) for t in ids}
+
+    # ---- F = Complex: inputs are complex128 arrays (interleaved re, im in memory)
+    def fill_z(self, seed, tensor_id, scale, count, first=0):
+        out = np.empty(count, dtype=np.complex128)
+        self.L.oracle_fill_z(seed, tensor_id, scale, first, count, _d(out))
+        return out
+
+    def inputs_z(self, No, Nv, seed=12345, scale=0.1, with_J=False):
+        ids = [EPS_I, EPS_A, TAI, TABIJ, VABIJ, VIJKA, VABCI] + ([JIJKA, JABCI] if with_J else [])
+        sz = tensor_sizes(No, Nv)
+        return {t: self.fill_z(seed, t, scale, sz[t]) for t in ids}
+
+    @staticmethod
+    def tuple_slices_z(No, Nv, t, abc, J=False):
+        """the 18 complex slices of one tuple (numpy views of the column-major tensors)"""
+        a, b, c = abc
+        T = t[TABIJ].reshape((Nv, Nv, No, No), order="F")
+        Vij = t[VABIJ].reshape((Nv, Nv, No, No), order="F")
+        Vp = t[JABCI if J else VABCI].reshape((Nv, Nv, Nv, No), order="F")
+        Vh = t[JIJKA if J else VIJKA].reshape((No, No, No, Nv), order="F")
+        flat = lambda x: np.ascontiguousarray(x.reshape(-1, order="F"))
+        S = {}
+        for nm, (x, y) in dict(VAB=(a, b), VAC=(a, c), VBC=(b, c), VBA=(b, a), VCA=(c, a), VCB=(c, b)).items():
+            S[nm] = flat(Vp[x, y])
+        for nm, x in dict(HA=a, HB=b, HC=c).items():
+            S[nm] = flat(Vh[:, :, :, x])
+        for nm, x in dict(TA=a, TB=b, TC=c).items():
+            S[nm] = flat(T[x])
+        for nm, (x, y) in dict(TAB=(a, b), TAC=(a, c), TBC=(b, c)).items():
+            S[nm] = flat(T[x, y])
+        for nm, (x, y) in dict(VABij=(a, b), VACij=(a, c), VBCij=(b, c)).items():
+            S[nm] = flat(Vij[x, y])
+        return S
+
+    def doubles_z(self, No, Nv, S):
+        out = np.empty(No ** 3, dtype=np.complex128)
+        self.L.oracle_doubles_z(No, Nv, *[_d(S[k]) for k in self.DOUBLES_ORDER], _d(out))
+        return out
+
+    def singles_z(self, No, Nv, abc, Tai, S, Tijk):
+        Z = Tijk.copy()
+        self.L.oracle_singles_z(No, Nv, abc[0], abc[1], abc[2], _d(Tai), _d(S["VABij"]),
+                                _d(S["VACij"]), _d(S["VBCij"]), _d(Z))
+        return Z
+
+    def energy_distinct_z(self, epsabc, No, epsi, Tijk, Zijk):
+        return self.L.oracle_energy_distinct_z(epsabc, No, _d(epsi), _d(Tijk), _d(Zijk))
+
+    def energy_same_z(self, epsabc, No, epsi, Tijk, Zijk):
+        return self.L.oracle_energy_same_z(epsabc, No, _d(epsi), _d(Tijk), _d(Zijk))
+
+    def tuple_energy_z(self, No, Nv, t, abc, want_cubes=False):
+        T = np.empty(No ** 3, dtype=np.complex128) if want_cubes else None
+        Z = np.empty(No ** 3, dtype=np.complex128) if want_cubes else None
+        ct = C.c_double(0)
+        e = self.L.oracle_tuple_energy_z(
+            No, Nv, _d(t[EPS_I]), _d(t[EPS_A]), _d(t[TAI]), _d(t[TABIJ]), _d(t[VABIJ]),
+            _d(t[VIJKA]), _d(t[VABCI]), _d(t.get(JIJKA)), _d(t.get(JABCI)),
+            abc[0], abc[1], abc[2], _d(T), _d(Z), C.cast(C.byref(ct), _dp))
+        return (e, ct.value, T, Z) if want_cubes else (e, ct.value)
+
+    def run_z(self, No, Nv, t, tuples=None):
+        e, ct = C.c_double(0), C.c_double(0)
+        tp, n = (None, 0)
+        if tuples is not None:
+            tuples = np.ascontiguousarray(tuples, dtype=np.uint64)
+            tp, n = tuples.ctypes.data_as(_up), len(tuples)
+        self.L.oracle_run_z(No, Nv, _d(t[EPS_I]), _d(t[EPS_A]), _d(t[TAI]), _d(t[TABIJ]),
+                            _d(t[VABIJ]), _d(t[VIJKA]), _d(t[VABCI]), _d(t.get(JIJKA)),
+                            _d(t.get(JABCI)), tp, n, C.cast(C.byref(e), _dp), C.cast(C.byref(ct), _dp))
+        return e.value, ct.value
 
     # ---- slices
     def slice_TA(self, No, Nv, Tabij, x):
@@ -217,6 +298,15 @@ class Reference:
         for f in (L.ref_energy_distinct, L.ref_energy_same):
             f.restype = C.c_double
             f.argtypes = [C.c_double, C.c_long, _dp, _dp, _dp]
+        self.has_complex = hasattr(L, "ref_run_z")
+        if self.has_complex:
+            L.ref_run_z.restype = C.c_int
+            L.ref_run_z.argtypes = L.ref_run.argtypes
+            L.ref_doubles_z.argtypes = [C.c_long, C.c_long] + [_dp] * 18
+            L.ref_singles_z.argtypes = [C.c_long] * 5 + [_dp] * 5
+            for f in (L.ref_energy_distinct_z, L.ref_energy_same_z):
+                f.restype = C.c_double
+                f.argtypes = [C.c_double, C.c_long, _dp, _dp, _dp]
         L.ref_group_and_sort.restype = C.c_long
         L.ref_group_and_sort.argtypes = [C.c_long, C.c_long, C.c_long, _up, C.c_long]
         L.ref_all_tuples.restype = C.c_long
@@ -235,6 +325,36 @@ class Reference:
 
     def chrono(self, name):
         return self.L.ref_chrono(name.encode())
+
+    # ---- F = Complex (complex128 arrays)
+    def run_z(self, No, Nv, t, max_iterations=0):
+        e, ct = C.c_double(0), C.c_double(0)
+        err = C.create_string_buffer(512)
+        rc = self.L.ref_run_z(No, Nv, _d(t[EPS_I]), _d(t[EPS_A]), _d(t[TAI]), _d(t[TABIJ]),
+                              _d(t[VABIJ]), _d(t[VIJKA]), _d(t[VABCI]), _d(t.get(JIJKA)),
+                              _d(t.get(JABCI)), max_iterations, C.cast(C.byref(e), _dp),
+                              C.cast(C.byref(ct), _dp), err, 512)
+        if rc:
+            raise RuntimeError("reference threw: " + err.value.decode())
+        return e.value, ct.value
+
+    def doubles_z(self, No, Nv, S):
+        out = np.empty(No ** 3, dtype=np.complex128)
+        tb, vh = np.empty(No ** 3, dtype=np.complex128), np.empty(No ** 3, dtype=np.complex128)
+        self.L.ref_doubles_z(No, Nv, *[_d(S[k]) for k in Oracle.DOUBLES_ORDER], _d(out), _d(tb), _d(vh))
+        return out
+
+    def singles_z(self, No, Nv, abc, Tai, S, Tijk):
+        Z = Tijk.copy()
+        self.L.ref_singles_z(No, Nv, abc[0], abc[1], abc[2], _d(Tai), _d(S["VABij"]),
+                             _d(S["VACij"]), _d(S["VBCij"]), _d(Z))
+        return Z
+
+    def energy_distinct_z(self, epsabc, No, epsi, Tijk, Zijk):
+        return self.L.ref_energy_distinct_z(epsabc, No, _d(epsi), _d(Tijk), _d(Zijk))
+
+    def energy_same_z(self, epsabc, No, epsi, Tijk, Zijk):
+        return self.L.ref_energy_same_z(epsabc, No, _d(epsi), _d(Tijk), _d(Zijk))
 
     def doubles(self, No, Nv, S, scratch=None):
         out = np.empty(No ** 3)

@@ -17,10 +17,11 @@
 using namespace atrip;
 
 namespace {
-CTF::Tensor<double> *wrap(CTF::World &w, std::vector<int> lens, const double *src) {
+template <typename F = double>
+CTF::Tensor<F> *wrap(CTF::World &w, std::vector<int> lens, const F *src) {
   std::vector<int> syms(lens.size(), NS);
-  auto *t = new CTF::Tensor<double>((int)lens.size(), lens.data(), syms.data(), w);
-  std::memcpy(t->data, src, sizeof(double) * t->size);
+  auto *t = new CTF::Tensor<F>((int)lens.size(), lens.data(), syms.data(), w);
+  std::memcpy(t->data, src, sizeof(F) * t->size);
   return t;
 }
 bool initialised = false;
@@ -133,6 +134,107 @@ double ref_energy_same(double epsabc, long No, double *epsi, double *Tijk,
                        double *Zijk) {
   double e = 0;
   get_energy_same<double>(epsabc, (size_t)No, epsi, Tijk, Zijk, &e);
+  return e;
+}
+
+// ---- F = Complex (reference instantiations Atrip.cxx:1136, Equations.cxx:730-795).
+// Arrays are interleaved (re, im) doubles = std::complex<double> memory layout.
+
+// atrip::Atrip::run<Complex> (reference Atrip.cxx:65-1133), same options as ref_run
+int ref_run_z(int No, int Nv, const double *epsi, const double *epsa,
+              const double *Tai, const double *Tabij, const double *Vabij,
+              const double *Vijka, const double *Vabci, const double *Jijka,
+              const double *Jabci, long max_iterations, double *energy,
+              double *ct_energy, char *err, int errlen) {
+  try {
+    CTF::World world(MPI_COMM_WORLD);
+    if (!initialised) {
+      Atrip::init(world.comm);
+      initialised = true;
+    }
+    Atrip::chrono.clear();
+    auto Z = [](const double *p) { return reinterpret_cast<const Complex *>(p); };
+    auto *ei = wrap<Complex>(world, {No}, Z(epsi));
+    auto *ea = wrap<Complex>(world, {Nv}, Z(epsa));
+    auto *tph = wrap<Complex>(world, {Nv, No}, Z(Tai));
+    auto *tpphh = wrap<Complex>(world, {Nv, Nv, No, No}, Z(Tabij));
+    auto *vpphh = wrap<Complex>(world, {Nv, Nv, No, No}, Z(Vabij));
+    auto *vhhhp = wrap<Complex>(world, {No, No, No, Nv}, Z(Vijka));
+    auto *vppph = wrap<Complex>(world, {Nv, Nv, Nv, No}, Z(Vabci));
+    CTF::Tensor<Complex> *jhhhp = Jijka ? wrap<Complex>(world, {No, No, No, Nv}, Z(Jijka)) : nullptr;
+    CTF::Tensor<Complex> *jppph = Jabci ? wrap<Complex>(world, {Nv, Nv, Nv, No}, Z(Jabci)) : nullptr;
+    auto in = Atrip::Input<Complex>()
+                  .with_epsilon_i(ei)
+                  .with_epsilon_a(ea)
+                  .with_Tai(tph)
+                  .with_Tabij(tpphh)
+                  .with_Vabij(vpphh)
+                  .with_Vijka(vhhhp)
+                  .with_Vabci(vppph)
+                  .with_Jijka(jhhhp)
+                  .with_Jabci(jppph)
+                  .with_delete_Vppph(false)
+                  .with_tuples_distribution(
+                      Atrip::Input<Complex>::TuplesDistribution::GROUP_AND_SORT)
+                  .with_max_iterations((size_t)max_iterations)
+                  .with_iteration_mod(-1)
+                  .with_percentage_mod(-1)
+                  .with_read_checkpoint_if_exists(false)
+                  .with_checkpoint_at_every_iteration((size_t)1 << 60);
+    auto out = Atrip::run<Complex>(in);
+    *energy = out.energy;
+    *ct_energy = out.ct_energy;
+    delete ei;
+    delete ea;
+    delete tph;
+    delete tpphh;
+    delete vpphh;
+    delete vhhhp;
+    delete vppph;
+    delete jhhhp;
+    delete jppph;
+    return 0;
+  } catch (const char *m) {
+    std::strncpy(err, m, errlen - 1);
+  } catch (std::string const &m) {
+    std::strncpy(err, m.c_str(), errlen - 1);
+  } catch (std::exception const &e) {
+    std::strncpy(err, e.what(), errlen - 1);
+  }
+  return 1;
+}
+
+// atrip::doubles_contribution<Complex> (reference Equations.cxx:455-728)
+void ref_doubles_z(long No, long Nv, double *VAB, double *VAC, double *VBC,
+                   double *VBA, double *VCA, double *VCB, double *HA, double *HB,
+                   double *HC, double *TA, double *TB, double *TC, double *TAB,
+                   double *TAC, double *TBC, double *Tijk, double *tbuf,
+                   double *vhhh) {
+  auto Z = [](double *p) { return reinterpret_cast<Complex *>(p); };
+  doubles_contribution<Complex>((size_t)No, (size_t)Nv, Z(VAB), Z(VAC), Z(VBC), Z(VBA), Z(VCA),
+                                Z(VCB), Z(HA), Z(HB), Z(HC), Z(TA), Z(TB), Z(TC), Z(TAB), Z(TAC),
+                                Z(TBC), Z(Tijk), Z(tbuf), Z(vhhh));
+}
+
+// atrip::singles_contribution<Complex> (reference Equations.cxx:387-426)
+void ref_singles_z(long No, long Nv, long a, long b, long c, double *Tph,
+                   double *VABij, double *VACij, double *VBCij, double *Zijk) {
+  auto Z = [](double *p) { return reinterpret_cast<Complex *>(p); };
+  singles_contribution<Complex>((size_t)No, (size_t)Nv, (size_t)a, (size_t)b, (size_t)c, Z(Tph),
+                                Z(VABij), Z(VACij), Z(VBCij), Z(Zijk));
+}
+
+// atrip::get_energy_distinct / get_energy_same <Complex> (reference Equations.cxx:101-238)
+double ref_energy_distinct_z(double epsabc, long No, double *epsi, double *Tijk, double *Zijk) {
+  auto Z = [](double *p) { return reinterpret_cast<Complex *>(p); };
+  double e = 0;
+  get_energy_distinct<Complex>(Complex(epsabc), (size_t)No, Z(epsi), Z(Tijk), Z(Zijk), &e);
+  return e;
+}
+double ref_energy_same_z(double epsabc, long No, double *epsi, double *Tijk, double *Zijk) {
+  auto Z = [](double *p) { return reinterpret_cast<Complex *>(p); };
+  double e = 0;
+  get_energy_same<Complex>(Complex(epsabc), (size_t)No, Z(epsi), Z(Tijk), Z(Zijk), &e);
   return e;
 }
 

@@ -29,6 +29,15 @@ TUPLES = [  # (No, Nv, seed, scale, [(a,b,c)...])  per-tuple values through the 
     (33, 40, 7, 0.05, [(0, 1, 2), (4, 4, 9), (4, 9, 9), (10, 20, 30)]),
     (40, 48, 3, 0.05, [(0, 1, 2), (1, 1, 47), (5, 17, 33)]),
 ]
+RUNS_Z = [  # F = Complex: (No, Nv, seed, scale, with_J) through Atrip::run<Complex>
+    (4, 8, 12345, 0.1, False), (4, 8, 777, 0.1, True), (5, 11, 12345, 0.05, False), (7, 13, 99, 0.05, True),
+    (10, 24, 12345, 0.02, False), (16, 24, 5, 0.01, False),
+]
+TUPLES_Z = [  # F = Complex: per-tuple values through the reference L1 functions
+    (10, 24, 12345, 0.1, [(0, 1, 2), (0, 0, 1), (3, 3, 7), (2, 5, 5), (0, 23, 23), (21, 22, 23), (5, 11, 17)]),
+    (13, 29, 4242, 0.1, [(0, 1, 2), (5, 5, 6), (5, 6, 6), (26, 27, 28)]),
+    (33, 36, 7, 0.05, [(0, 1, 2), (4, 4, 9), (10, 20, 30)]),
+]
 DISTS = [(8, 1), (13, 2), (13, 3), (21, 4), (40, 8), (33, 5)]  # (Nv, n_nodes)
 
 
@@ -62,6 +71,30 @@ def main():
                                       Zsample=[float(Z[i]).hex() for i in idx]))
             print("tuple", No, Nv, abc, e)
         out["tuples"].append(rec)
+    out["complex_runs"], out["complex_tuples"] = [], []
+    for No, Nv, seed, scale, J in RUNS_Z:
+        t = o.inputs_z(No, Nv, seed=seed, scale=scale, with_J=J)
+        e, ct = r.run_z(No, Nv, t)
+        out["complex_runs"].append(dict(No=No, Nv=Nv, seed=seed, scale=scale, with_J=J, energy=e.hex(),
+                                        ct_energy=ct.hex()))
+        print("complex run", No, Nv, seed, J, e, ct)
+    for No, Nv, seed, scale, tl in TUPLES_Z:
+        t = o.inputs_z(No, Nv, seed=seed, scale=scale)
+        rec = dict(No=No, Nv=Nv, seed=seed, scale=scale, tuples=[])
+        for abc in tl:
+            S = o.tuple_slices_z(No, Nv, t, abc)
+            T = r.doubles_z(No, Nv, S)
+            Z = r.singles_z(No, Nv, abc, t[TAI], S, T)
+            epsabc = float((t[EPS_A][abc[0]] + t[EPS_A][abc[1]] + t[EPS_A][abc[2]]).real)
+            same = (abc[0] == abc[1]) != (abc[1] == abc[2])
+            e = (r.energy_same_z if same else r.energy_distinct_z)(epsabc, No, t[EPS_I], T, Z)
+            idx = [0, 1, No, No * No, No ** 3 // 2, No ** 3 - 1]
+            hx = lambda z: [float(z.real).hex(), float(z.imag).hex()]
+            rec["tuples"].append(dict(abc=list(abc), energy=e.hex(), Tsum=hx(T.sum()), Zsum=hx(Z.sum()),
+                                      Tabsmax=float(np.abs(T).max()).hex(),
+                                      Tsample=[hx(T[i]) for i in idx], Zsample=[hx(Z[i]) for i in idx]))
+            print("complex tuple", No, Nv, abc, e)
+        out["complex_tuples"].append(rec)
     for Nv, n in DISTS:
         rec = dict(Nv=Nv, n_nodes=n, nodes=[])
         for me in range(n):
