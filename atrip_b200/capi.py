@@ -24,10 +24,12 @@ SYMBOLS = [
     "atrip_b200_synth_to_host", "atrip_b200_batch_tuples", "atrip_b200_host_plan", "atrip_b200_device_count",
     "atrip_b200_comm_unique_id", "atrip_b200_comm_init", "atrip_b200_allreduce", "atrip_b200_last_exchange",
     "atrip_b200_host_slice_slot", "atrip_b200_host_shard_sizes", "atrip_b200_host_plan_batch",
-    "atrip_b200_host_cache_need", "atrip_b200_host_local_slot",
+    "atrip_b200_host_cache_need", "atrip_b200_host_local_slot", "atrip_b200_host_store_source",
+    "atrip_b200_host_energy_z", "atrip_b200_debug_cubes_checksum",
 ]
 
 NAIVE, GROUP_AND_SORT = 0, 1
+FIELD_REAL, FIELD_COMPLEX = 0, 1
 TRANSPORT_DEFAULT, TRANSPORT_NCCL, TRANSPORT_P2P = 0, 1, 2
 TA, VIJKA, VABCI, TABIJ, VABIJ = 100, 101, 200, 201, 202
 VABCI_T = 203  # host-side name of the transposed-hole twin (x,x)' of a diagonal pair slice
@@ -40,7 +42,7 @@ class EngineError(RuntimeError):
 class Config(C.Structure):
     _fields_ = [("device", C.c_int32), ("rank", C.c_int32), ("nranks", C.c_int32), ("with_J", C.c_int32),
                 ("No", C.c_int64), ("Nv", C.c_int64), ("batch_tuples", C.c_int64),
-                ("resident", C.c_int32), ("transport", C.c_int32)]
+                ("resident", C.c_int32), ("transport", C.c_int32), ("field", C.c_int32)]
 
 
 def lib_path():
@@ -111,6 +113,10 @@ def load_library():
     L.atrip_b200_comm_init.argtypes = [ctx, C.c_void_p]
     L.atrip_b200_allreduce.argtypes = [ctx, _dp, C.c_int32]
     L.atrip_b200_last_exchange.argtypes = [ctx, _dp]
+    L.atrip_b200_host_store_source.argtypes = [C.c_int32, C.c_int64, C.c_int64, C.c_int32, C.c_int64, C.c_int64,
+                                               C.c_int64, C.c_int64, _dp]
+    L.atrip_b200_host_energy_z.argtypes = [C.c_int64, C.c_double, _dp, _dp, _dp, C.c_int32]
+    L.atrip_b200_host_energy_z.restype = C.c_double
     L.atrip_b200_measure_dmma_peak.argtypes = [C.c_int32, _dp]
     L.atrip_b200_synth_to_host.argtypes = [C.c_int32, C.c_uint64, C.c_int32, C.c_double, C.c_uint64, C.c_uint64, _dp]
     _lib = L
@@ -219,21 +225,40 @@ def comm_unique_id():
 
 
 def _ptr(a):
-    """double* of a host buffer: numpy float64 array, or an int address (e.g. pinned torch storage)"""
+    """double* of a host buffer: numpy float64 (or complex128 = interleaved doubles) array, or an int
+    address (e.g. pinned torch storage)"""
     if a is None:
         return None
     if isinstance(a, int):
         return C.cast(a, _dp)
-    assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"] or a.flags["F_CONTIGUOUS"]
+    assert a.dtype in (np.float64, np.complex128) and (a.flags["C_CONTIGUOUS"] or a.flags["F_CONTIGUOUS"])
     return a.ctypes.data_as(_dp)
+
+
+def store_source(store, No, Nv, a, x, y, row, kappa):
+    """complex layout: (tensor, part, sign, element) held by a store element (host-only)"""
+    L = load_library()
+    out = (C.c_double * 4)()
+    if L.atrip_b200_host_store_source(store, No, Nv, a, x, y, row, kappa, out) != 0:
+        raise EngineError(L.atrip_b200_last_error().decode())
+    return int(out[0]), int(out[1]), out[2], int(out[3])
+
+
+def host_energy_z(No, epsabc, eps_i, Tijk, Zijk, same):
+    """complex tuple energy through the device kernel's per-point function, on the host"""
+    L = load_library()
+    return L.atrip_b200_host_energy_z(No, epsabc, _ptr(eps_i), _ptr(Tijk), _ptr(Zijk), int(same))
 
 
 class Engine:
     def __init__(self, No, Nv, device=0, rank=0, nranks=1, with_J=False, batch_tuples=0, resident=True,
-                 transport=0):
+                 transport=0, field=FIELD_REAL):
         self.L = load_library()
         self.No, self.Nv = int(No), int(Nv)
-        cfg = Config(device, rank, nranks, int(with_J), No, Nv, batch_tuples, int(resident), int(transport))
+        self.field = int(field)
+        self.dtype = np.complex128 if self.field == FIELD_COMPLEX else np.float64
+        cfg = Config(device, rank, nranks, int(with_J), No, Nv, batch_tuples, int(resident), int(transport),
+                     self.field)
         self.ctx = C.c_void_p()
         self._ck(self.L.atrip_b200_create(C.byref(self.ctx), C.byref(cfg)))
 
@@ -311,8 +336,8 @@ class Engine:
 
     def tuple_debug(self, a, b, c, cubes=True):
         n = self.No ** 3
-        T = np.empty(n) if cubes else None
-        Z = np.empty(n) if cubes else None
+        T = np.empty(n, dtype=self.dtype) if cubes else None
+        Z = np.empty(n, dtype=self.dtype) if cubes else None
         e = C.c_double(0)
         self._ck(self.L.atrip_b200_tuple_debug(self.ctx, a, b, c, _ptr(T), _ptr(Z), C.byref(e)))
         return e.value, T, Z
@@ -320,7 +345,7 @@ class Engine:
     def read_slice(self, kind, x, y=0):
         No, Nv = self.No, self.Nv
         n = {TA: Nv * No * No, VIJKA: No ** 3, VABCI: Nv * No, TABIJ: No * No, VABIJ: No * No}[kind]
-        out = np.empty(n)
+        out = np.empty(n, dtype=self.dtype)
         self._ck(self.L.atrip_b200_read_slice(self.ctx, kind, x, y, _ptr(out)))
         return out
 
@@ -338,6 +363,13 @@ class Engine:
         out = (C.c_double * 2)()
         self.L.atrip_b200_last_exchange(self.ctx, out)
         return dict(bytes=out[0], messages=int(out[1]))
+
+    def cubes_checksum(self):
+        """debug: integer checksum of the class cubes of the last batch"""
+        h = C.c_uint64(0)
+        self.L.atrip_b200_debug_cubes_checksum.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+        self._ck(self.L.atrip_b200_debug_cubes_checksum(self.ctx, C.byref(h)))
+        return h.value
 
     def last_timing(self):
         out = (C.c_double * 6)()

@@ -67,15 +67,17 @@ struct ContractParams {
   int ntuples;
   int ownedA, ownedB;      // slots >= owned address the cache maps (schedule.hpp)
   const TupleRec *recs;    // the batch: tuple + store slots of its slices (built on the host)
-  double *R;               // [ntuples][3][cube_stride] class cubes C_k, C_j, C_i (8x8x8-blocked)
+  double *R;               // class cubes C_k, C_j, C_i (8x8x8-blocked) of tuple t at R + t tuple_stride
   size_t cube_stride;      // doubles per stored cube = ceil(No/8)^3 * 512
+  size_t tuple_stride;     // 3 cube_stride; complex field: 6 cube_stride (Re cubes, then Im cubes --
+                           // the Im launch gets R + 3 cube_stride and the variant-1 tensor maps)
 };
 
 __host__ __device__ inline size_t contract_stage_bytes(int arows, int NI) {
   return (size_t)(arows + NI * 8) * 128;
 }
 
-template <int MI, int NI, int MAXT, bool KTAIL>
+template <int MI, int NI, int MAXT>
 __global__ void __launch_bounds__(MAXT, 1)
 contract_kernel(const __grid_constant__ ContractMaps M, const ContractParams P) {
   extern __shared__ unsigned char smem_raw[];
@@ -189,16 +191,25 @@ contract_kernel(const __grid_constant__ ContractMaps M, const ContractParams P) 
 #pragma unroll
           for (int j = 0; j < NI; j++) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
       };
-      if (!KTAIL || (ch != P.nk - 1 && ch != nchunks - 1)) {
+      if (ch != P.nk - 1 && ch != nchunks - 1) {
 #pragma unroll
         for (int s = 0; s < 4; s++) kstep(cs[s]);
       } else {
-        // KTAIL: last chunk of an operand pair when Kp > No + Nv -- only the k-steps that hold
-        // data (the rest of the 16-wide chunk is zero padding)
+        // last chunk of an operand pair: only the k-steps that hold data (the rest of the 16-wide
+        // chunk is zero padding; last_steps = 4 when Kp has no padding)
         kstep(cs[0]);
         if (P.last_steps > 1) kstep(cs[1]);
         if (P.last_steps > 2) kstep(cs[2]);
+        if (P.last_steps > 3) kstep(cs[3]);
       }
+      // Hand the stage back only after every fragment load of it has delivered its data.  The
+      // loads are consumed by DMMAs, which wait for their operands at issue, so "after all DMMAs
+      // of the stage in program order" is sufficient -- but ptxas may move the arrive (it has no
+      // register dependency) anywhere inside a basic block: a former straight-line variant of
+      // this loop body (no tail branch) had the arrive scheduled between the last LDS and its
+      // DMMAs and produced run-to-run different cubes (profiles/r01_ring_release_race.txt).  The
+      // two-way branch above ends the basic block that holds the loads; tools/check_sass_order.py
+      // (run by tests/test_host.py) asserts  last DMMA < WARPSYNC < arrive  in every instantiation.
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty_bar[stage]);
       if (++stage == P.nstages) { stage = 0; phase ^= 1; }
@@ -208,7 +219,7 @@ contract_kernel(const __grid_constant__ ContractMaps M, const ContractParams P) 
     // Every class cube is stored at Tijk's own (i,j,k) -- class 0 (u,v,n) = (i,j,k), class 1
     // (i,k,j), class 2 (j,k,i) -- in the 8x8x8-blocked layout kernel 2 streams (cube_offset):
     // the offset is separable, off(i,j,k) = gi(i) + gj(j) + gk(k).
-    double *Rc = P.R + ((size_t)tup * 3 + cls) * P.cube_stride;
+    double *Rc = P.R + (size_t)tup * P.tuple_stride + (size_t)cls * P.cube_stride;
     const int u0 = (mt % P.utiles) * P.tu, v0 = (mt / P.utiles) * P.tv;
     const unsigned nb = (unsigned)(P.No + 7) >> 3;
     // tile stride / in-tile stride of the coordinate the column index n plays in this class

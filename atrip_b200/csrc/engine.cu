@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include "contraction.cuh"
 #include "reduction.cuh"
+#include "reduction_z.cuh"
 #include "schedule.hpp"
 #include "stores.cuh"
 #include "tuples.hpp"
@@ -43,11 +44,9 @@ struct Fail {
 // ------------------------------------------------------------------ contraction kernel registry
 struct KernelVariant {
   int MI, NI, maxt;
-  const void *fn, *fn_ktail;  // fn_ktail: skips the zero-padded k-steps when Kp > No + Nv
+  const void *fn;
 };
-#define VARIANT(mi, ni, maxt)                                                       \
-  KernelVariant{mi, ni, maxt, (const void *)contract_kernel<mi, ni, maxt, false>,  \
-                (const void *)contract_kernel<mi, ni, maxt, true>}
+#define VARIANT(mi, ni, maxt) KernelVariant{mi, ni, maxt, (const void *)contract_kernel<mi, ni, maxt>}
 // accumulators take 4*MI*NI registers; the thread cap follows from the 64K register file
 const KernelVariant kVariants[] = {
     VARIANT(2, 1, 512), VARIANT(3, 1, 512), VARIANT(4, 1, 512), VARIANT(5, 1, 512),
@@ -163,6 +162,8 @@ constexpr int REC_RING = 4;  // batches the host may run ahead of the device
 struct atrip_b200_ctx {
   atrip_b200_config cfg{};
   int No = 0, Nv = 0, Kp = 0;
+  int cplx = 0;   // field: 0 FP64 real, 1 std::complex<double> (stores.cuh "complex field")
+  int Klen = 0;   // valid contraction length: No + Nv (real), 2 (No + Nv) (complex); Kp = Klen padded to 16
   int nsm = 0;
   size_t smem_limit = 0;
   // contraction (high priority); reduction of the previous batch (low priority, runs beside the
@@ -197,7 +198,8 @@ struct atrip_b200_ctx {
 
   // kernel plan
   ContractPlan plan;
-  ContractMaps maps, mapsJ;
+  ContractMaps maps, mapsJ;    // real field / complex variant 0 ([Re A | -Im A] rows of the AX slices)
+  ContractMaps maps1, mapsJ1;  // complex variant 1 ([Im A | Re A] rows)
 
   // slice exchange
   ncclComm_t comm = nullptr;
@@ -219,27 +221,34 @@ struct atrip_b200_ctx {
   cudaEvent_t stage_ev[2]{};
 
   double timing[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int last_nt = 0, last_buf = 0;  // tuples and cube buffer of the last batch run (debug checksum)
 };
 
 namespace {
 
-StoreDims dims_of(const atrip_b200_ctx *c) { return StoreDims{c->No, c->Nv, c->Kp}; }
+StoreDims dims_of(const atrip_b200_ctx *c) { return StoreDims{c->No, c->Nv, c->Kp, c->cplx}; }
 
+// doubles per slice.  Complex field: an AX slice holds both variants, a VIJ slice is interleaved
 size_t slice_elems(const atrip_b200_ctx *c, int kind) {
-  const size_t No = c->No, Kp = c->Kp;
-  return kind == KA ? No * No * Kp : (kind == KB ? No * Kp : No * No);
+  const size_t No = c->No, Kp = c->Kp, z = c->cplx ? 2 : 1;
+  return kind == KA ? z * No * No * Kp : (kind == KB ? No * Kp : z * No * No);
 }
+size_t esz(const atrip_b200_ctx *c) { return c->cplx ? 2 : 1; }        // doubles per tensor element
+int ncubes(const atrip_b200_ctx *c) { return c->cplx ? 6 : 3; }        // class cubes per tuple
 
+// variant: which half of a complex AX slice the A maps address (0 for the real field)
 void build_maps(atrip_b200_ctx *c, double *AX, uint64_t nA, double *BY, uint64_t nB, CUtensorMap *tA,
-                CUtensorMap *tAT, CUtensorMap *tB) {
+                CUtensorMap *tAT, CUtensorMap *tB, int variant = 0) {
   const uint64_t No = c->No, Kp = c->Kp;
   {
+    const uint64_t slot = slice_elems(c, KA) * 8;  // bytes between slices (complex: two variants each)
     const uint64_t dims[4] = {Kp, No, No, std::max<uint64_t>(nA, 1)};
-    const uint64_t strP[3] = {Kp * 8, No * Kp * 8, No * No * Kp * 8};
-    const uint64_t strT[3] = {No * Kp * 8, Kp * 8, No * No * Kp * 8};
+    const uint64_t strP[3] = {Kp * 8, No * Kp * 8, slot};
+    const uint64_t strT[3] = {No * Kp * 8, Kp * 8, slot};
     const uint32_t box[4] = {KC, (uint32_t)c->plan.tu, (uint32_t)c->plan.tv, 1};
-    make_map(tA, AX, 4, dims, strP, box);
-    make_map(tAT, AX, 4, dims, strT, box);
+    double *base = AX + (size_t)variant * No * No * Kp;
+    make_map(tA, base, 4, dims, strP, box);
+    make_map(tAT, base, 4, dims, strT, box);
   }
   {
     const uint64_t dims[3] = {Kp, No, std::max<uint64_t>(nB, 1)};
@@ -251,13 +260,16 @@ void build_maps(atrip_b200_ctx *c, double *AX, uint64_t nA, double *BY, uint64_t
 
 // (re)build all tensor maps: owned stores, and the fetch caches when there are any
 void build_all_maps(atrip_b200_ctx *c) {
-  build_maps(c, c->AX, c->owned[KA], c->BY, c->owned[KB], &c->maps.A, &c->maps.AT, &c->maps.B);
-  if (c->cA) build_maps(c, c->cA, 2 * c->cap[KA], c->cB, 2 * c->cap[KB], &c->maps.Ac, &c->maps.ATc, &c->maps.Bc);
-  else { c->maps.Ac = c->maps.A; c->maps.ATc = c->maps.AT; c->maps.Bc = c->maps.B; }
-  if (c->cfg.with_J) {
-    build_maps(c, c->AXJ, c->owned[KA], c->BYJ, c->owned[KB], &c->mapsJ.A, &c->mapsJ.AT, &c->mapsJ.B);
-    if (c->cAJ) build_maps(c, c->cAJ, 2 * c->cap[KA], c->cBJ, 2 * c->cap[KB], &c->mapsJ.Ac, &c->mapsJ.ATc, &c->mapsJ.Bc);
-    else { c->mapsJ.Ac = c->mapsJ.A; c->mapsJ.ATc = c->mapsJ.AT; c->mapsJ.Bc = c->mapsJ.B; }
+  for (int var = 0; var <= c->cplx; var++) {
+    ContractMaps &M = var ? c->maps1 : c->maps, &MJ = var ? c->mapsJ1 : c->mapsJ;
+    build_maps(c, c->AX, c->owned[KA], c->BY, c->owned[KB], &M.A, &M.AT, &M.B, var);
+    if (c->cA) build_maps(c, c->cA, 2 * c->cap[KA], c->cB, 2 * c->cap[KB], &M.Ac, &M.ATc, &M.Bc, var);
+    else { M.Ac = M.A; M.ATc = M.AT; M.Bc = M.B; }
+    if (c->cfg.with_J) {
+      build_maps(c, c->AXJ, c->owned[KA], c->BYJ, c->owned[KB], &MJ.A, &MJ.AT, &MJ.B, var);
+      if (c->cAJ) build_maps(c, c->cAJ, 2 * c->cap[KA], c->cBJ, 2 * c->cap[KB], &MJ.Ac, &MJ.ATc, &MJ.Bc, var);
+      else { MJ.Ac = MJ.A; MJ.ATc = MJ.AT; MJ.Bc = MJ.B; }
+    }
   }
 }
 
@@ -327,17 +339,17 @@ void stream_chunks(atrip_b200_ctx *c, const double *host, size_t nchunks, size_t
   CUDA_OK(cudaStreamSynchronize(c->stream));
 }
 
-// the padded contraction length has at least one whole k-step (4 kappa) of zeros
-bool has_ktail(const atrip_b200_ctx *c) { return c->Kp - (c->No + c->Nv) >= 4; }
-const void *contract_fn(const atrip_b200_ctx *c) { return has_ktail(c) ? c->plan.k->fn_ktail : c->plan.k->fn; }
+const void *contract_fn(const atrip_b200_ctx *c) { return c->plan.k->fn; }
 
-void launch_contract(atrip_b200_ctx *c, const TupleRec *d_recs, int ntuples, bool useJ, int buf) {
+// avar: AX variant read by this launch (complex field: 0 -> Re cubes, 1 -> Im cubes)
+void launch_contract(atrip_b200_ctx *c, const TupleRec *d_recs, int ntuples, bool useJ, int buf, int avar = 0) {
   ContractParams P;
   P.No = c->No;
   P.Nv = c->Nv;
   P.Kp = c->Kp;
   P.nk = c->Kp / KC;
-  P.last_steps = (c->No + c->Nv - (P.nk - 1) * KC + 3) / 4;
+  // k-steps of the last chunk that hold data (the kernel skips the zero padding behind them)
+  P.last_steps = std::max(1, std::min(4, (c->Klen - (P.nk - 1) * KC + 3) / 4));
   P.tu = c->plan.tu;
   P.tv = c->plan.tv;
   P.utiles = c->plan.utiles;
@@ -350,14 +362,16 @@ void launch_contract(atrip_b200_ctx *c, const TupleRec *d_recs, int ntuples, boo
   P.ownedA = (int)c->owned[KA];
   P.ownedB = (int)c->owned[KB];
   P.recs = d_recs;
-  P.R = useJ ? c->RJ[buf] : c->R[buf];
   P.cube_stride = cube_blocked_elems(c->No);
+  P.tuple_stride = ncubes(c) * P.cube_stride;
+  P.R = (useJ ? c->RJ[buf] : c->R[buf]) + (size_t)avar * 3 * P.cube_stride;
   const long long nitems = 3LL * P.mtiles * P.ntiles * ntuples;
   // NCCL transport: leave a few SMs to the send/recv kernels of the side stream, otherwise they
   // only run in the gaps between two persistent contraction launches
   const int grid = (int)std::min<long long>(c->nsm - c->comm_sms, nitems);
   if (grid <= 0) return;
-  void *args[2] = {useJ ? (void *)&c->mapsJ : (void *)&c->maps, (void *)&P};
+  ContractMaps *maps = useJ ? (avar ? &c->mapsJ1 : &c->mapsJ) : (avar ? &c->maps1 : &c->maps);
+  void *args[2] = {(void *)maps, (void *)&P};
   CUDA_OK(cudaLaunchKernel(contract_fn(c), dim3(grid), dim3((c->plan.nw + 1) * 32), args, c->plan.smem, c->stream));
 }
 
@@ -391,6 +405,10 @@ ReduceParams reduce_params(atrip_b200_ctx *c, const TupleRec *d_recs, int ntuple
     if (score > best_score + 1e-9) { best_score = score; best = ns; }
   }
   P.nsplit = best;
+  if (const char *e = std::getenv("ATRIP_B200_NSPLIT")) {  // developer knob: force the orbit split
+    const int v = std::atoi(e);
+    if (v >= 1) P.nsplit = std::min(v, std::min(orbits, 64));
+  }
   return P;
 }
 
@@ -399,7 +417,11 @@ void launch_reduce(atrip_b200_ctx *c, const TupleRec *d_recs, int ntuples, bool 
   ReduceParams P = reduce_params(c, d_recs, ntuples, ct, buf);
   const size_t smem = reduce_smem_bytes(c->No, ct);
   const dim3 grid(ntuples, P.nsplit);
-  if (ct) reduce_kernel<true><<<grid, REDUCE_THREADS, smem, c->rstream>>>(P);
+  if (c->cplx) {
+    const size_t smz = reduce_z_smem_bytes(c->No, ct);
+    if (ct) reduce_z_kernel<true><<<grid, REDUCE_THREADS, smz, c->rstream>>>(P);
+    else reduce_z_kernel<false><<<grid, REDUCE_THREADS, smz, c->rstream>>>(P);
+  } else if (ct) reduce_kernel<true><<<grid, REDUCE_THREADS, smem, c->rstream>>>(P);
   else reduce_kernel<false><<<grid, REDUCE_THREADS, smem, c->rstream>>>(P);
   CUDA_OK(cudaGetLastError());
   accumulate_kernel<<<1, 256, 0, c->rstream>>>(c->e_tuple, ntuples * P.nsplit, total);
@@ -434,7 +456,12 @@ void create_impl(atrip_b200_ctx *c) {
   c->smem_limit = prop.sharedMemPerBlockOptin;
   c->No = (int)cfg.No;
   c->Nv = (int)cfg.Nv;
-  c->Kp = (int)((cfg.No + cfg.Nv + KC - 1) / KC * KC);
+  REQUIRE(cfg.field == 0 || cfg.field == 1, "field must be 0 (FP64 real) or 1 (FP64 complex)");
+  c->cplx = cfg.field;
+  c->Klen = (int)((cfg.No + cfg.Nv) * (c->cplx ? 2 : 1));
+  c->Kp = (c->Klen + KC - 1) / KC * KC;
+  if (const char *e = std::getenv("ATRIP_B200_KPAD"))  // developer knob: extra all-zero K chunks
+    c->Kp += KC * std::max(0, std::atoi(e));
   int prio_least = 0, prio_greatest = 0;
   CUDA_OK(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
   CUDA_OK(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_greatest));
@@ -455,6 +482,13 @@ void create_impl(atrip_b200_ctx *c) {
                                (int)reduce_smem_bytes(c->No, false)));
   CUDA_OK(cudaFuncSetAttribute((const void *)reduce_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)reduce_smem_bytes(c->No, true)));
+  if (c->cplx) {
+    REQUIRE(reduce_z_smem_bytes(c->No, true) <= c->smem_limit, "No too large for the complex reduction kernel");
+    CUDA_OK(cudaFuncSetAttribute((const void *)reduce_z_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)reduce_z_smem_bytes(c->No, false)));
+    CUDA_OK(cudaFuncSetAttribute((const void *)reduce_z_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)reduce_z_smem_bytes(c->No, true)));
+  }
 
   // ---- which slices live here: everything (replica) or the slices this rank owns
   const int sn = (cfg.resident || cfg.nranks == 1) ? 1 : cfg.nranks;
@@ -522,12 +556,12 @@ void create_impl(atrip_b200_ctx *c) {
     CUDA_OK(cudaMemsetAsync(c->AXJ, 0, axn * 8, c->stream));
     CUDA_OK(cudaMemsetAsync(c->BYJ, 0, byn * 8, c->stream));
   }
-  c->eps_i = dalloc<double>(No);
-  c->eps_a = dalloc<double>(Nv);
-  c->Tai = dalloc<double>(No * Nv);
+  c->eps_i = dalloc<double>(esz(c) * No);
+  c->eps_a = dalloc<double>(esz(c) * Nv);
+  c->Tai = dalloc<double>(esz(c) * No * Nv);
 
   // ---- work buffers: a batch keeps roughly 8 work items per SM in flight and <= 1 GiB of cubes
-  const size_t cube3 = 3 * cube_blocked_elems(c->No);
+  const size_t cube3 = ncubes(c) * cube_blocked_elems(c->No);
   long long batch = cfg.batch_tuples;
   if (batch <= 0) {
     const long long per_tuple = 3LL * c->plan.mtiles * c->plan.ntiles;
@@ -610,7 +644,32 @@ void destroy_impl(atrip_b200_ctx *c) {
 
 int grid_for(size_t n, int nsm) { return (int)std::min<size_t>((n + 255) / 256, (size_t)nsm * 16); }
 
+void fill_z_impl(atrip_b200_ctx *c, uint64_t seed, double scale) {
+  const StoreDims d = dims_of(c);
+  const size_t No = c->No;
+  const size_t nX = c->owned[KA], nB = c->owned[KB], nV = c->owned[KV];
+  fill_small_z_kernel<<<grid_for(No * (size_t)c->Nv, c->nsm), 256, 0, c->stream>>>(
+      c->eps_i, c->eps_a, c->Tai, d, synth_key(seed, T_EPS_I), synth_key(seed, T_EPS_A), synth_key(seed, T_TAI), scale);
+  fill_AX_z_kernel<<<grid_for(nX * slice_elems(c, KA), c->nsm), 256, 0, c->stream>>>(
+      c->AX, d, c->xlist, (int)nX, synth_key(seed, T_TABIJ), synth_key(seed, T_VIJKA), scale);
+  fill_BY_z_kernel<<<grid_for(nB * slice_elems(c, KB), c->nsm), 256, 0, c->stream>>>(
+      c->BY, d, c->ylist, c->zlist, c->tflag, nB, synth_key(seed, T_VABCI), synth_key(seed, T_TABIJ), scale);
+  fill_VIJ_z_kernel<<<grid_for(nV * slice_elems(c, KV), c->nsm), 256, 0, c->stream>>>(c->VIJ, d, c->vy, c->vz, nV,
+                                                                                     synth_key(seed, T_VABIJ), scale);
+  if (c->cfg.with_J) {
+    fill_AX_z_kernel<<<grid_for(nX * slice_elems(c, KA), c->nsm), 256, 0, c->stream>>>(
+        c->AXJ, d, c->xlist, (int)nX, synth_key(seed, T_TABIJ), synth_key(seed, T_JIJKA), scale);
+    fill_BY_z_kernel<<<grid_for(nB * slice_elems(c, KB), c->nsm), 256, 0, c->stream>>>(
+        c->BYJ, d, c->ylist, c->zlist, c->tflag, nB, synth_key(seed, T_JABCI), synth_key(seed, T_TABIJ), scale);
+    c->have_J = true;
+  }
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  c->stores_dirty = true;
+}
+
 void fill_impl(atrip_b200_ctx *c, uint64_t seed, double scale) {
+  if (c->cplx) return fill_z_impl(c, seed, scale);
   const StoreDims d = dims_of(c);
   const size_t No = c->No;
   const size_t nX = c->owned[KA], nB = c->owned[KB], nV = c->owned[KV];
@@ -638,8 +697,14 @@ void load_Tabij_impl(atrip_b200_ctx *c, const double *T) {
   const StoreDims d = dims_of(c);
   const size_t NvNv = (size_t)c->Nv * c->Nv;
   const dim3 grid((c->Nv + 31) / 32, (c->Nv + 31) / 32), block(32, 8);
-  stream_chunks(c, T, (size_t)c->No * c->No, NvNv, [&](size_t k, const double *dev) {
+  stream_chunks(c, T, (size_t)c->No * c->No, esz(c) * NvNv, [&](size_t k, const double *dev) {
     const int p = (int)(k % c->No), q = (int)(k / c->No);
+    if (c->cplx) {
+      const int g = grid_for(NvNv, c->nsm);
+      ingest_Tabij_z_kernel<<<g, 256, 0, c->stream>>>(dev, d, p, q, c->AX, c->xtab, c->BY, c->btab);
+      if (c->cfg.with_J) ingest_Tabij_z_kernel<<<g, 256, 0, c->stream>>>(dev, d, p, q, c->AXJ, c->xtab, c->BYJ, c->btab);
+      return;
+    }
     ingest_Tabij_kernel<<<grid, block, 0, c->stream>>>(dev, d, p, q, c->AX, c->xtab, c->BY, c->btab);
     if (c->cfg.with_J)
       ingest_Tabij_kernel<<<grid, block, 0, c->stream>>>(dev, d, p, q, c->AXJ, c->xtab, c->BYJ, c->btab);
@@ -650,20 +715,23 @@ void load_Tabij_impl(atrip_b200_ctx *c, const double *T) {
 void load_hhhp_impl(atrip_b200_ctx *c, const double *V, double *AX) {
   const StoreDims d = dims_of(c);
   const size_t cube = (size_t)c->No * c->No * c->No;
-  const size_t xper = std::max<size_t>(1, std::min<size_t>(c->Nv, (size_t)(32u << 20) / (cube * 8)));
+  const size_t z = esz(c);
+  const size_t xper = std::max<size_t>(1, std::min<size_t>(c->Nv, (size_t)(32u << 20) / (z * cube * 8)));
   const size_t nchunks = (c->Nv + xper - 1) / xper;
-  ensure_stage(c, xper * cube);
+  ensure_stage(c, z * xper * cube);
+  auto ingest = [&](const double *dev, size_t x0, size_t nx) {
+    if (c->cplx)
+      ingest_Vijka_z_kernel<<<grid_for(nx * cube, c->nsm), 256, 0, c->stream>>>(dev, d, (int)x0, (int)nx, AX, c->xtab);
+    else
+      ingest_Vijka_kernel<<<grid_for(nx * cube, c->nsm), 256, 0, c->stream>>>(dev, d, (int)x0, (int)nx, AX, c->xtab);
+  };
   // the last chunk may be shorter: stream_chunks copies full chunks, so handle the tail by hand
   const size_t full = c->Nv / xper;
-  stream_chunks(c, V, full, xper * cube, [&](size_t k, const double *dev) {
-    ingest_Vijka_kernel<<<grid_for(xper * cube, c->nsm), 256, 0, c->stream>>>(dev, d, (int)(k * xper), (int)xper, AX,
-                                                                            c->xtab);
-  });
+  stream_chunks(c, V, full, z * xper * cube, [&](size_t k, const double *dev) { ingest(dev, k * xper, xper); });
   if (full < nchunks) {
     const size_t x0 = full * xper, nx = c->Nv - x0;
-    CUDA_OK(cudaMemcpyAsync(c->d_stage[0], V + x0 * cube, nx * cube * 8, cudaMemcpyHostToDevice, c->stream));
-    ingest_Vijka_kernel<<<grid_for(nx * cube, c->nsm), 256, 0, c->stream>>>(c->d_stage[0], d, (int)x0, (int)nx, AX,
-                                                                          c->xtab);
+    CUDA_OK(cudaMemcpyAsync(c->d_stage[0], V + z * x0 * cube, z * nx * cube * 8, cudaMemcpyHostToDevice, c->stream));
+    ingest(c->d_stage[0], x0, nx);
     CUDA_OK(cudaStreamSynchronize(c->stream));
   }
   CUDA_OK(cudaGetLastError());
@@ -672,9 +740,13 @@ void load_hhhp_impl(atrip_b200_ctx *c, const double *V, double *AX) {
 void load_Vabij_impl(atrip_b200_ctx *c, const double *V) {
   const StoreDims d = dims_of(c);
   const size_t NvNv = (size_t)c->Nv * c->Nv;
-  stream_chunks(c, V, (size_t)c->No * c->No, NvNv, [&](size_t k, const double *dev) {
-    ingest_Vabij_kernel<<<grid_for(NvNv, c->nsm), 256, 0, c->stream>>>(dev, d, (int)(k % c->No), (int)(k / c->No),
-                                                                     c->VIJ, c->vtab);
+  stream_chunks(c, V, (size_t)c->No * c->No, esz(c) * NvNv, [&](size_t k, const double *dev) {
+    if (c->cplx)
+      ingest_Vabij_z_kernel<<<grid_for(NvNv, c->nsm), 256, 0, c->stream>>>(dev, d, (int)(k % c->No), (int)(k / c->No),
+                                                                         c->VIJ, c->vtab);
+    else
+      ingest_Vabij_kernel<<<grid_for(NvNv, c->nsm), 256, 0, c->stream>>>(dev, d, (int)(k % c->No), (int)(k / c->No),
+                                                                       c->VIJ, c->vtab);
   });
   CUDA_OK(cudaGetLastError());
 }
@@ -685,21 +757,26 @@ void load_ppph_impl(atrip_b200_ctx *c, const double *V, double *BY) {
   // chunk = up to 16 consecutive E for one r: Vabci[:, :, E0.., r]; E blocks never straddle r
   const int Nv = c->Nv;
   const int eblocks = (Nv + KC - 1) / KC;
-  ensure_stage(c, (size_t)KC * NvNv);
+  const size_t z = esz(c);
+  ensure_stage(c, z * (size_t)KC * NvNv);
   const dim3 grid((unsigned)((NvNv + 31) / 32)), block(32, 8);
   int slot = 0;
   for (int r = 0; r < c->No; r++)
     for (int eb = 0; eb < eblocks; eb++, slot ^= 1) {
       const int E0 = eb * KC, ne = std::min(KC, Nv - E0);
-      const double *src = V + ((size_t)E0 + (size_t)r * Nv) * NvNv;
-      const size_t n = (size_t)ne * NvNv;
+      const double *src = V + z * ((size_t)E0 + (size_t)r * Nv) * NvNv;
+      const size_t n = z * (size_t)ne * NvNv;
       CUDA_OK(cudaEventSynchronize(c->stage_ev[slot]));
       if (!is_pinned(src)) {
         std::memcpy(c->h_stage[slot], src, n * 8);
         src = c->h_stage[slot];
       }
       CUDA_OK(cudaMemcpyAsync(c->d_stage[slot], src, n * 8, cudaMemcpyHostToDevice, c->stream));
-      ingest_Vabci_kernel<<<grid, block, 0, c->stream>>>(c->d_stage[slot], d, E0, ne, r, BY, c->btab);
+      if (c->cplx)
+        ingest_Vabci_z_kernel<<<grid_for((size_t)ne * NvNv, c->nsm), 256, 0, c->stream>>>(c->d_stage[slot], d, E0, ne, r,
+                                                                                        BY, c->btab);
+      else
+        ingest_Vabci_kernel<<<grid, block, 0, c->stream>>>(c->d_stage[slot], d, E0, ne, r, BY, c->btab);
       CUDA_OK(cudaEventRecord(c->stage_ev[slot], c->stream));
     }
   CUDA_OK(cudaStreamSynchronize(c->stream));
@@ -876,17 +953,23 @@ void run_list(atrip_b200_ctx *c, const Tuple *list, int64_t count, double *energ
     //      the same datapath, profiles/r01_fused_reducers_rejected_ncu.txt; the second stream only
     //      lets the reduction fill the ragged tail of the next contraction launch)
     const int buf = (int)(k & 1);
+    c->last_nt = nt;
+    c->last_buf = buf;
     if (k >= 2) CUDA_OK(cudaStreamWaitEvent(c->stream, c->rdone[(k - 2) & 3], 0));  // buffer reduced
     // per-kernel events around the first batches only: contraction [2,3], reduction [4,5]
     const bool sample = sampled < 4;
     if (sample) CUDA_OK(cudaEventRecord(c->ev[2], c->stream));
-    launch_contract(c, dr, nt, false, buf);
-    n_contract++;
+    for (int var = 0; var <= c->cplx; var++) {  // complex field: Re cubes, then Im cubes
+      launch_contract(c, dr, nt, false, buf, var);
+      n_contract++;
+    }
     if (sample) CUDA_OK(cudaEventRecord(c->ev[3], c->stream));
     CUDA_OK(cudaEventRecord(c->evV[k & 3], c->stream));
     if (ct) {
-      launch_contract(c, dr, nt, true, buf);
-      n_contract++;
+      for (int var = 0; var <= c->cplx; var++) {
+        launch_contract(c, dr, nt, true, buf, var);
+        n_contract++;
+      }
       CUDA_OK(cudaEventRecord(c->evJ[k & 3], c->stream));
     }
     CUDA_OK(cudaEventRecord(c->cdone[k & 3], c->stream));
@@ -968,17 +1051,18 @@ void tuple_debug_impl(atrip_b200_ctx *c, int64_t a, int64_t b, int64_t cc, doubl
   double e = 0;
   const uint64_t slot = c->rec_uses % REC_RING;  // the ring slot run_list is about to use
   run_list(c, &one, 1, &e, nullptr);
-  const size_t cube = (size_t)c->No * c->No * c->No;
+  const size_t cube = (size_t)c->No * c->No * c->No, cd = esz(c) * cube;  // complex: interleaved cubes
   double *dT = nullptr, *dZ = nullptr;
-  if (Tijk) dT = dalloc<double>(cube);
-  if (Zijk) dZ = dalloc<double>(cube);
+  if (Tijk) dT = dalloc<double>(cd);
+  if (Zijk) dZ = dalloc<double>(cd);
   if (Tijk || Zijk) {
     ReduceParams P = reduce_params(c, c->d_recs + slot * c->batch, 1, false, 0);
-    cubes_kernel<<<grid_for(cube, c->nsm), 256, 0, c->stream>>>(P, 0, dT, dZ);
+    if (c->cplx) cubes_z_kernel<<<grid_for(cube, c->nsm), 256, 0, c->stream>>>(P, 0, dT, dZ);
+    else cubes_kernel<<<grid_for(cube, c->nsm), 256, 0, c->stream>>>(P, 0, dT, dZ);
     CUDA_OK(cudaGetLastError());
   }
-  if (Tijk) CUDA_OK(cudaMemcpyAsync(Tijk, dT, cube * 8, cudaMemcpyDeviceToHost, c->stream));
-  if (Zijk) CUDA_OK(cudaMemcpyAsync(Zijk, dZ, cube * 8, cudaMemcpyDeviceToHost, c->stream));
+  if (Tijk) CUDA_OK(cudaMemcpyAsync(Tijk, dT, cd * 8, cudaMemcpyDeviceToHost, c->stream));
+  if (Zijk) CUDA_OK(cudaMemcpyAsync(Zijk, dZ, cd * 8, cudaMemcpyDeviceToHost, c->stream));
   CUDA_OK(cudaStreamSynchronize(c->stream));
   if (dT) cudaFree(dT);
   if (dZ) cudaFree(dZ);
@@ -1006,15 +1090,16 @@ void read_slice_impl(atrip_b200_ctx *c, int kind, int64_t x, int64_t y, double *
     n = No * No;
     const int64_t s = m.localV(x, y);
     REQUIRE(s >= 0, "this rank does not own that slice");
-    vij = c->VIJ + (size_t)s * No * No;
+    vij = c->VIJ + (size_t)s * slice_elems(c, KV);
   } else {
     throw Fail{"unknown slice kind"};
   }
   if (kind == 201) REQUIRE(y >= 0 && y < (int64_t)Nv, "slice index y out of range");
-  double *d = dalloc<double>(n);
-  read_slice_kernel<<<grid_for(n, c->nsm), 256, 0, c->stream>>>(kind, dims_of(c), ax, by, vij, (int)y, d);
+  double *d = dalloc<double>(esz(c) * n);
+  if (c->cplx) read_slice_z_kernel<<<grid_for(n, c->nsm), 256, 0, c->stream>>>(kind, dims_of(c), ax, by, vij, (int)y, d);
+  else read_slice_kernel<<<grid_for(n, c->nsm), 256, 0, c->stream>>>(kind, dims_of(c), ax, by, vij, (int)y, d);
   CUDA_OK(cudaGetLastError());
-  CUDA_OK(cudaMemcpyAsync(out, d, n * 8, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(cudaMemcpyAsync(out, d, esz(c) * n * 8, cudaMemcpyDeviceToHost, c->stream));
   CUDA_OK(cudaStreamSynchronize(c->stream));
   cudaFree(d);
 }
@@ -1094,6 +1179,14 @@ __global__ void synth_range_kernel(double *out, uint64_t key, int tensor_id, dou
   }
 }
 
+// debug: order-independent checksum (sum of the raw bit patterns as integers) of n doubles
+__global__ void checksum_kernel(const double *p, size_t n, unsigned long long *out) {
+  unsigned long long s = 0;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    s += (unsigned long long)__double_as_longlong(p[i]);
+  atomicAdd(out, s);
+}
+
 template <typename F>
 int guarded(atrip_b200_ctx *c, F f) {
   try {
@@ -1147,12 +1240,12 @@ int atrip_b200_destroy(atrip_b200_ctx *c) {
 
 int atrip_b200_set_epsilon(atrip_b200_ctx *c, const double *ei, const double *ea) {
   return guarded(c, [&] {
-    CUDA_OK(cudaMemcpy(c->eps_i, ei, sizeof(double) * c->No, cudaMemcpyHostToDevice));
-    CUDA_OK(cudaMemcpy(c->eps_a, ea, sizeof(double) * c->Nv, cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(c->eps_i, ei, sizeof(double) * esz(c) * c->No, cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(c->eps_a, ea, sizeof(double) * esz(c) * c->Nv, cudaMemcpyHostToDevice));
   });
 }
 int atrip_b200_set_Tai(atrip_b200_ctx *c, const double *Tai) {
-  return guarded(c, [&] { CUDA_OK(cudaMemcpy(c->Tai, Tai, sizeof(double) * c->No * c->Nv, cudaMemcpyHostToDevice)); });
+  return guarded(c, [&] { CUDA_OK(cudaMemcpy(c->Tai, Tai, sizeof(double) * esz(c) * c->No * c->Nv, cudaMemcpyHostToDevice)); });
 }
 int atrip_b200_load_Tabij(atrip_b200_ctx *c, const double *T) { return guarded(c, [&] { c->stores_dirty = true; load_Tabij_impl(c, T); }); }
 int atrip_b200_load_Vabij(atrip_b200_ctx *c, const double *V) { return guarded(c, [&] { c->stores_dirty = true; load_Vabij_impl(c, V); }); }
@@ -1220,6 +1313,20 @@ int atrip_b200_tuple_debug(atrip_b200_ctx *c, int64_t a, int64_t b, int64_t cc, 
 int atrip_b200_read_slice(atrip_b200_ctx *c, int32_t kind, int64_t x, int64_t y, double *out) {
   return guarded(c, [&] { read_slice_impl(c, kind, x, y, out); });
 }
+int atrip_b200_debug_cubes_checksum(atrip_b200_ctx *c, uint64_t *out) {
+  return guarded(c, [&] {
+    unsigned long long *d = dalloc<unsigned long long>(1);
+    CUDA_OK(cudaMemsetAsync(d, 0, 8, c->stream));
+    const size_t n = (size_t)c->last_nt * ncubes(c) * cube_blocked_elems(c->No);
+    if (n) checksum_kernel<<<1024, 256, 0, c->stream>>>(c->R[c->last_buf], n, d);
+    CUDA_OK(cudaGetLastError());
+    unsigned long long h = 0;
+    CUDA_OK(cudaMemcpyAsync(&h, d, 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    cudaFree(d);
+    *out = h;
+  });
+}
 int atrip_b200_last_timing(const atrip_b200_ctx *c, double *out6) {
   for (int i = 0; i < 6; i++) out6[i] = c->timing[i];
   return 0;
@@ -1249,7 +1356,7 @@ int64_t atrip_b200_kp(const atrip_b200_ctx *c) { return c->Kp; }
 int64_t atrip_b200_batch_tuples(const atrip_b200_ctx *c) { return c->batch; }
 double atrip_b200_flops_per_tuple(const atrip_b200_ctx *c) {
   const double No = c->No, Nv = c->Nv;
-  return 12.0 * No * No * No * (No + Nv);
+  return 12.0 * No * No * No * (No + Nv) * (c->cplx ? 4.0 : 1.0);  // x4 for complex, Atrip.cxx:578-580
 }
 
 int atrip_b200_measure_dmma_peak(int32_t device, double *tflops) {
@@ -1404,6 +1511,25 @@ int atrip_b200_host_cache_need(int64_t Nv, int32_t rank, int32_t nranks, const u
   for (int64_t i = 0; i < n; i++) t[i] = Tuple{abc[3 * i], abc[3 * i + 1], abc[3 * i + 2]};
   cache_need(m, t.data(), (size_t)n, (size_t)batch, out3);
   return 0;
+}
+
+int atrip_b200_host_store_source(int32_t store, int64_t No, int64_t Nv, int32_t a, int64_t x, int64_t y,
+                                 int64_t row, int64_t kappa, double *out4) {
+  if (No < 1 || Nv < 1 || x < 0 || x >= Nv || row < 0 || kappa < 0 || !out4 || (store != 0 && store != 1)) {
+    g_error = "atrip_b200_host_store_source: bad arguments";
+    return 1;
+  }
+  const SourceRef r = store == 0 ? ax_source_z((int)No, (int)Nv, a, (size_t)x, (size_t)row, (size_t)kappa)
+                                 : by_source_z((int)No, (int)Nv, (size_t)x, (size_t)y, a, (size_t)row, (size_t)kappa);
+  out4[0] = r.tensor;
+  out4[1] = r.part;
+  out4[2] = r.sign;
+  out4[3] = (double)r.lin;
+  return 0;
+}
+double atrip_b200_host_energy_z(int64_t No, double epsabc, const double *eps_i, const double *Tijk,
+                                const double *Zijk, int32_t same) {
+  return host_energy_z((int)No, epsabc, eps_i, Tijk, Zijk, same != 0);
 }
 
 }  // extern "C"

@@ -21,6 +21,7 @@ namespace ab {
 
 struct StoreDims {
   int No, Nv, Kp;
+  int cplx = 0;  // 1: F = std::complex<double> (planes along kappa, see "complex field" below)
 };
 
 // ------------------------------------------------------------------ synthetic fill (device)
@@ -174,6 +175,259 @@ __global__ void ingest_Vabci_kernel(const double *chunk, StoreDims d, int E0, in
         if (s2 >= 0) BY[((size_t)s2 * d.No + r) * d.Kp + E0 + e] = v;
       }
     }
+  }
+}
+
+// ------------------------------------------------------------------ complex field (F = Complex)
+// The complex contraction C = A B (A = [T_x ; -conj(H_x)], B = [V_yz ; T_yz], reference
+// Equations.cxx:620-680 with MAYBE_CONJ on the hole integrals, :623-648) runs on the SAME real
+// DMMA kernel with the contraction index doubled, Kh = No + Nv:
+//     Re C = [ Re A | -Im A ] [ Re B ; Im B ]          Im C = [ Im A | Re A ] [ Re B ; Im B ]
+//   AX [xslot][variant][m][Kp]   variant 0: kappa < Kh: Re A[kappa];  Kh <= kappa < 2Kh: -Im A[kappa - Kh]
+//                                variant 1: kappa < Kh: Im A[kappa];  Kh <= kappa < 2Kh:  Re A[kappa - Kh]
+//   BY [bslot][r][Kp]            kappa < Kh: Re B[kappa];             Kh <= kappa < 2Kh:  Im B[kappa - Kh]
+//   VIJ[vslot][i + j No]         interleaved (re, im)
+// with A[kk] = T_x[kk,p,q] (kk < Nv) or -conj(H_x[q,p,kk-Nv]), B[kk] as in the real case, and
+// Kp = 2 Kh rounded up to 16.  Both variants of a slice are contiguous, so the slice exchange moves
+// them as one slice.  Synthetic complex tensors: element e = (synth(2e), synth(2e+1)).
+
+// what a store element holds: part (0 re, 1 im) of element `lin` of source tensor `tensor`
+// (0 = padding, 1 = Tabij, 2 = Vijka/Jijka, 3 = Vabci/Jabci), times `sign`
+struct SourceRef {
+  int tensor;
+  int part;
+  double sign;
+  unsigned long long lin;
+};
+
+__host__ __device__ inline SourceRef ax_source_z(int No_, int Nv_, int variant, size_t x, size_t m, size_t kap) {
+  const size_t No = No_, Nv = Nv_, Kh = No + Nv;
+  SourceRef r{0, 0, 0.0, 0ull};
+  if (kap >= 2 * Kh) return r;
+  const int plane = kap >= Kh;
+  const size_t kk = plane ? kap - Kh : kap;
+  // (Re A, Im A) of this kk; variant 0 wants (Re, -Im), variant 1 wants (Im, Re)
+  const int want_im = (variant == 0) ? plane : !plane;
+  const double vsign = (variant == 0 && plane) ? -1.0 : 1.0;
+  const size_t p = m % No, q = m / No;
+  if (kk < Nv) {  // A = T_x[E,p,q]
+    r.tensor = 1;
+    r.lin = x + kk * Nv + p * Nv * Nv + q * Nv * Nv * No;
+    r.part = want_im;
+    r.sign = vsign;
+  } else {  // A = -conj(H_x[q,p,L]): Re A = -Re H, Im A = +Im H
+    const size_t L = kk - Nv;
+    r.tensor = 2;
+    r.lin = q + p * No + L * No * No + x * No * No * No;
+    r.part = want_im;
+    r.sign = want_im ? vsign : -vsign;
+  }
+  return r;
+}
+
+__host__ __device__ inline SourceRef by_source_z(int No_, int Nv_, size_t y, size_t z, int tflag, size_t rr,
+                                                 size_t kap) {
+  const size_t No = No_, Nv = Nv_, Kh = No + Nv;
+  SourceRef r{0, 0, 0.0, 0ull};
+  if (kap >= 2 * Kh) return r;
+  r.part = kap >= Kh;
+  r.sign = 1.0;
+  const size_t kk = r.part ? kap - Kh : kap;
+  if (kk < Nv) {
+    r.tensor = 3;
+    r.lin = y + z * Nv + kk * Nv * Nv + rr * Nv * Nv * Nv;
+  } else {
+    const size_t L = kk - Nv;
+    const bool transposed = (y > z) || (y == z && tflag);
+    r.tensor = 1;
+    r.lin = transposed ? z + y * Nv + rr * Nv * Nv + L * Nv * Nv * No : y + z * Nv + L * Nv * Nv + rr * Nv * Nv * No;
+  }
+  return r;
+}
+
+__global__ void fill_AX_z_kernel(double *AX, StoreDims d, const int *xlist, int nx, uint64_t keyT, uint64_t keyH,
+                                 double scale) {
+  const size_t per = (size_t)d.No * d.No * d.Kp, total = per * 2 * nx;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const size_t sv = e / per, r = e - sv * per;
+    const size_t s = sv >> 1, m = r / d.Kp, kap = r - m * d.Kp;
+    const SourceRef sr = ax_source_z(d.No, d.Nv, (int)(sv & 1), (size_t)xlist[s], m, kap);
+    double v = 0.0;
+    if (sr.tensor) v = __dmul_rn(sr.sign, synth_val(sr.tensor == 1 ? keyT : keyH, 2 * sr.lin + sr.part, scale));
+    AX[e] = v;
+  }
+}
+
+__global__ void fill_BY_z_kernel(double *BY, StoreDims d, const int *ylist, const int *zlist, const int *tflag,
+                                 size_t nb, uint64_t keyV, uint64_t keyT, double scale) {
+  const size_t per = (size_t)d.No * d.Kp, total = per * nb;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const size_t s = e / per, rr = e - s * per;
+    const size_t r = rr / d.Kp, kap = rr - r * d.Kp;
+    const SourceRef sr = by_source_z(d.No, d.Nv, (size_t)ylist[s], (size_t)zlist[s], tflag[s], r, kap);
+    double v = 0.0;
+    if (sr.tensor) v = synth_val(sr.tensor == 3 ? keyV : keyT, 2 * sr.lin + sr.part, scale);
+    BY[e] = v;
+  }
+}
+
+// VIJ (interleaved complex) and Tai: plain doubled index; eps: (real-case value, 0)
+__global__ void fill_VIJ_z_kernel(double *VIJ, StoreDims d, const int *ylist, const int *zlist, size_t nv,
+                                  uint64_t key, double scale) {
+  const size_t per = 2 * (size_t)d.No * d.No, total = per * nv;
+  const size_t Nv = d.Nv, No = d.No;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const size_t s = e / per, r2 = e - s * per, r = r2 >> 1;
+    const size_t i = r % No, j = r / No;
+    const size_t lin = (size_t)ylist[s] + (size_t)zlist[s] * Nv + i * Nv * Nv + j * Nv * Nv * No;
+    VIJ[e] = synth_val(key, 2 * lin + (r2 & 1), scale);
+  }
+}
+
+__global__ void fill_small_z_kernel(double *eps_i, double *eps_a, double *Tai, StoreDims d, uint64_t kI, uint64_t kA,
+                                    uint64_t kT, double scale) {
+  const size_t n = (size_t)d.No + d.Nv + (size_t)d.No * d.Nv;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+    if (e < (size_t)d.No) {
+      eps_i[2 * e] = __dadd_rn(-2.0, __dmul_rn(1.5, synth_u(kI, e)));
+      eps_i[2 * e + 1] = 0.0;
+    } else if (e < (size_t)d.No + d.Nv) {
+      const size_t a = e - d.No;
+      eps_a[2 * a] = __dadd_rn(0.5, __dmul_rn(3.5, synth_u(kA, a)));
+      eps_a[2 * a + 1] = 0.0;
+    } else {
+      const size_t t = e - d.No - d.Nv;
+      Tai[2 * t] = synth_val(kT, 2 * t, scale);
+      Tai[2 * t + 1] = synth_val(kT, 2 * t + 1, scale);
+    }
+  }
+}
+
+// ---- ingest of interleaved-complex host chunks (one thread per source element; the same chunking
+//      as the real kernels above, chunk element e at doubles [2e, 2e+1])
+
+// chunk = Tabij[:, :, p, q]
+__global__ void ingest_Tabij_z_kernel(const double *chunk, StoreDims d, int p, int q, double *AX, const int *xtab,
+                                      double *BY, const int *btab) {
+  const size_t Nv = d.Nv, No = d.No, Kp = d.Kp, Kh = No + Nv, n = Nv * Nv;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+    const size_t al = e % Nv, be = e / Nv;
+    const double tr = chunk[2 * e], ti = chunk[2 * e + 1];
+    const int s = xtab[al];
+    if (s >= 0) {  // A[kk = be] = T_al[be,p,q]
+      double *row0 = AX + (((size_t)s * 2 + 0) * No * No + p + (size_t)q * No) * Kp;
+      double *row1 = AX + (((size_t)s * 2 + 1) * No * No + p + (size_t)q * No) * Kp;
+      row0[be] = tr;
+      row0[Kh + be] = -ti;
+      row1[be] = ti;
+      row1[Kh + be] = tr;
+    }
+    if (al <= be) {  // hole part of B, as in ingest_Tabij_kernel
+      const int s1 = btab[al + be * Nv];
+      if (s1 >= 0) {
+        double *row = BY + ((size_t)s1 * No + q) * Kp;
+        row[Nv + p] = tr;
+        row[Kh + Nv + p] = ti;
+      }
+      const int s2 = btab[al == be ? Nv * Nv + al : be + al * Nv];
+      if (s2 >= 0) {
+        double *row = BY + ((size_t)s2 * No + p) * Kp;
+        row[Nv + q] = tr;
+        row[Kh + Nv + q] = ti;
+      }
+    }
+  }
+}
+
+// chunk = Vijka[:, :, :, x0 .. x0+nx): A[kk = Nv + L] = -conj(Vijka[q,p,L,x])
+__global__ void ingest_Vijka_z_kernel(const double *chunk, StoreDims d, int x0, int nx, double *AX, const int *xtab) {
+  const size_t No = d.No, Nv = d.Nv, Kh = No + Nv, cube = No * No * No, total = cube * nx;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const size_t xs = e / cube, r = e - xs * cube;
+    const size_t L = r % No, m = r / No, p = m % No, q = m / No;
+    const int s = xtab[x0 + xs];
+    if (s < 0) continue;
+    const size_t src = xs * cube + q + p * No + L * No * No;
+    const double hr = chunk[2 * src], hi = chunk[2 * src + 1];  // Re A = -hr, Im A = +hi
+    double *row0 = AX + (((size_t)s * 2 + 0) * No * No + m) * d.Kp;
+    double *row1 = AX + (((size_t)s * 2 + 1) * No * No + m) * d.Kp;
+    row0[Nv + L] = -hr;
+    row0[Kh + Nv + L] = -hi;
+    row1[Nv + L] = hi;
+    row1[Kh + Nv + L] = -hr;
+  }
+}
+
+// chunk = Vabij[:, :, i, j]
+__global__ void ingest_Vabij_z_kernel(const double *chunk, StoreDims d, int i, int j, double *VIJ, const int *vtab) {
+  const size_t n = (size_t)d.Nv * d.Nv;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+    const int s = vtab[e];
+    if (s < 0) continue;
+    double *dst = VIJ + 2 * ((size_t)s * d.No * d.No + i + (size_t)j * d.No);
+    dst[0] = chunk[2 * e];
+    dst[1] = chunk[2 * e + 1];
+  }
+}
+
+// chunk = Vabci[:, :, E0 .. E0+ne, r]
+__global__ void ingest_Vabci_z_kernel(const double *chunk, StoreDims d, int E0, int ne, int r, double *BY,
+                                      const int *btab) {
+  const size_t Nv = d.Nv, No = d.No, Kh = No + Nv, NvNv = Nv * Nv, total = NvNv * ne;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const size_t pr = e % NvNv, el = e / NvNv;
+    const double vr = chunk[2 * e], vi = chunk[2 * e + 1];
+    const int s = btab[pr];
+    if (s >= 0) {
+      double *row = BY + ((size_t)s * No + r) * d.Kp;
+      row[E0 + el] = vr;
+      row[Kh + E0 + el] = vi;
+    }
+    const size_t y = pr % Nv, z = pr / Nv;
+    if (y == z) {
+      const int s2 = btab[NvNv + y];
+      if (s2 >= 0) {
+        double *row = BY + ((size_t)s2 * No + r) * d.Kp;
+        row[E0 + el] = vr;
+        row[Kh + E0 + el] = vi;
+      }
+    }
+  }
+}
+
+// read back a slice in the reference layout, interleaved complex; same kinds as read_slice_kernel.
+// AXx points at the slice's variant 0 ([Re A | -Im A] rows); VIJxy is interleaved.
+__global__ void read_slice_z_kernel(int kind, StoreDims d, const double *AXx, const double *BYxy,
+                                    const double *VIJxy, int y, double *out) {
+  const size_t No = d.No, Nv = d.Nv, Kp = d.Kp, Kh = No + Nv;
+  size_t n = 0;
+  if (kind == 100) n = Nv * No * No;
+  else if (kind == 101) n = No * No * No;
+  else if (kind == 200) n = Nv * No;
+  else n = No * No;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+    double re, im;
+    if (kind == 100) {  // TX[E + p Nv + q Nv No] = A[m][E]
+      const size_t E = e % Nv, m = e / Nv;
+      re = AXx[m * Kp + E];
+      im = -AXx[m * Kp + Kh + E];
+    } else if (kind == 101) {  // HX[p + q No + L No^2]: A[(q + p No)][Nv + L] = -conj(H)
+      const size_t p = e % No, q = (e / No) % No, L = e / (No * No);
+      re = -AXx[(q + p * No) * Kp + Nv + L];
+      im = -AXx[(q + p * No) * Kp + Kh + Nv + L];  // plane 1 holds -Im A = -Im H
+    } else if (kind == 200) {
+      const size_t E = e % Nv, r = e / Nv;
+      re = BYxy[r * Kp + E];
+      im = BYxy[r * Kp + Kh + E];
+    } else if (kind == 201) {
+      re = AXx[e * Kp + y];
+      im = -AXx[e * Kp + Kh + y];
+    } else {
+      re = VIJxy[2 * e];
+      im = VIJxy[2 * e + 1];
+    }
+    out[2 * e] = re;
+    out[2 * e + 1] = im;
   }
 }
 

@@ -49,21 +49,25 @@ void ok(int rc, const char *what) {
 // full column-major contents of a CTF tensor on this rank.  The dense single-process shim
 // exposes its storage; a real (distributed) CTF tensor is gathered with read_all, which is what
 // the reference does for the replicated tensors (Atrip.cxx:179-181).
+// For F = Complex `ptr` addresses interleaved (re, im) doubles -- std::complex<double>'s own memory
+// layout, which is how the C-ABI takes complex tensors (atrip_b200_config.field = 1).
+template <typename F>
 struct HostView {
   const double *ptr = nullptr;
-  std::vector<double> owned;
+  std::vector<F> owned;
 };
-HostView view(CTF::Tensor<double> *t) {
-  HostView v;
+template <typename F>
+HostView<F> view(CTF::Tensor<F> *t) {
+  HostView<F> v;
   if (!t) return v;
 #ifdef ATRIP_B200_DENSE_CTF_HPP
-  v.ptr = t->data;
+  v.ptr = reinterpret_cast<const double *>(t->data);
 #else
   int64_t n = 1;
   for (int i = 0; i < t->order; i++) n *= t->lens[i];
   v.owned.resize((size_t)n);
   t->read_all(v.owned.data());
-  v.ptr = v.owned.data();
+  v.ptr = reinterpret_cast<const double *>(v.owned.data());
 #endif
   return v;
 }
@@ -75,10 +79,12 @@ struct EngineHandle {
   }
 };
 
-}  // namespace
-
-template <>
-Atrip::Output Atrip::run<double>(Atrip::Input<double> const &in) {
+// Atrip::run<F> for F = double and F = Complex: the engine computes both fields, the host logic is
+// the same (the reference's is one template, Atrip.cxx:65-1133)
+template <typename F>
+Atrip::Output run_on_engine(Atrip::Input<F> const &in) {
+  using Output = Atrip::Output;
+  constexpr bool is_cplx = traits::is_complex<F>::value;
   if (!in.ei || !in.ea || !in.Tph || !in.Tpphh || !in.Vpphh || !in.Vhhhp || !in.Vppph)
     throw std::string("atrip: epsilon_i, epsilon_a, Tai, Tabij, Vabij, Vijka and Vabci are all required");
   const size_t No = (size_t)in.ei->lens[0], Nv = (size_t)in.ea->lens[0];  // Atrip.cxx:72-73
@@ -101,6 +107,7 @@ Atrip::Output Atrip::run<double>(Atrip::Input<double> const &in) {
   cfg.No = (int64_t)No;
   cfg.Nv = (int64_t)Nv;
   cfg.batch_tuples = 0;
+  cfg.field = is_cplx ? 1 : 0;
   // several ranks: every GPU stores the slices it owns and fetches the rest from its peers over
   // NCCL (the reference's SliceUnion sources + MPI fetches); ATRIP_B200_REPLICATE=1 keeps a full
   // replica per GPU instead (small problems)
@@ -120,10 +127,10 @@ Atrip::Output Atrip::run<double>(Atrip::Input<double> const &in) {
 
   {  // replicated tensors (Atrip.cxx:176-215); Tai is negated for the ijkabc algorithm (:183-187)
     Seconds t;
-    HostView ei = view(in.ei), ea = view(in.ea), tph = view(in.Tph);
+    auto ei = view(in.ei), ea = view(in.ea), tph = view(in.Tph);
     ok(atrip_b200_set_epsilon(eng.ctx, ei.ptr, ea.ptr), "set_epsilon");
     if (in.ijkabc) {
-      std::vector<double> neg(tph.ptr, tph.ptr + No * Nv);
+      std::vector<double> neg(tph.ptr, tph.ptr + (is_cplx ? 2 : 1) * No * Nv);
       for (auto &x : neg) x = -x;
       ok(atrip_b200_set_Tai(eng.ctx, neg.data()), "set_Tai");
     } else {
@@ -131,24 +138,24 @@ Atrip::Output Atrip::run<double>(Atrip::Input<double> const &in) {
     }
     // the four big tensors -> HBM stores (replaces the five SliceUnion ctors, Atrip.cxx:277-332)
     {
-      HostView v = view(in.Vppph);
+      auto v = view(in.Vppph);
       ok(atrip_b200_load_Vabci(eng.ctx, v.ptr), "load_Vabci");
     }
     if (in.delete_Vppph) delete in.Vppph;  // Atrip.cxx:310
     {
-      HostView v = view(in.Tpphh);
+      auto v = view(in.Tpphh);
       ok(atrip_b200_load_Tabij(eng.ctx, v.ptr), "load_Tabij");
     }
     {
-      HostView v = view(in.Vpphh);
+      auto v = view(in.Vpphh);
       ok(atrip_b200_load_Vabij(eng.ctx, v.ptr), "load_Vabij");
     }
     {
-      HostView v = view(in.Vhhhp);
+      auto v = view(in.Vhhhp);
       ok(atrip_b200_load_Vijka(eng.ctx, v.ptr), "load_Vijka");
     }
     if (with_J) {
-      HostView j1 = view(in.Jhhhp), j2 = view(in.Jppph);
+      auto j1 = view(in.Jhhhp), j2 = view(in.Jppph);
       ok(atrip_b200_load_Jijka(eng.ctx, j1.ptr), "load_Jijka");
       ok(atrip_b200_load_Jabci(eng.ctx, j2.ptr), "load_Jabci");
     }
@@ -157,7 +164,7 @@ Atrip::Output Atrip::run<double>(Atrip::Input<double> const &in) {
 
   {  // tuple distribution (Atrip.cxx:383-399)
     Seconds t;
-    ok(atrip_b200_build_tuples(eng.ctx, in.tuples_distribution == Input<double>::GROUP_AND_SORT ? 1 : 0),
+    ok(atrip_b200_build_tuples(eng.ctx, in.tuples_distribution == Atrip::Input<F>::GROUP_AND_SORT ? 1 : 0),
        "build_tuples");
     Atrip::chrono["tuples:build"] = t();
   }
@@ -245,11 +252,16 @@ Atrip::Output Atrip::run<double>(Atrip::Input<double> const &in) {
   return global;
 }
 
-// The complex instantiation exists so that drivers templated on the field link
-// (reference Atrip.cxx:1135-1136); the B200 engine implements the FP64 real case.
+}  // namespace
+
+// the reference's two instantiations (Atrip.cxx:1135-1136)
 template <>
-Atrip::Output Atrip::run<Complex>(Atrip::Input<Complex> const &) {
-  throw std::string("atrip (B200 build): run<Complex> is not implemented; only FP64 real (SURVEY.md 8f rank 4)");
+Atrip::Output Atrip::run<double>(Atrip::Input<double> const &in) {
+  return run_on_engine<double>(in);
+}
+template <>
+Atrip::Output Atrip::run<Complex>(Atrip::Input<Complex> const &in) {
+  return run_on_engine<Complex>(in);
 }
 
 }  // namespace atrip

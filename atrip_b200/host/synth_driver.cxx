@@ -1,7 +1,9 @@
 // Example/parity driver of the C++ API: builds CTF tensors holding the counter-based synthetic
 // inputs, calls atrip::Atrip::run<double> exactly like the reference's bench
 // (bench/main.cxx:345-391) and prints the energies in hex and decimal.
-//   synth_driver <No> <Nv> <seed> <scale> [max_iterations] [dist: group|naive] [cT]
+//   synth_driver <No> <Nv> <seed> <scale> [max_iterations] [dist: group|naive] [cT|T] [complex]
+// With "complex" the tensors are CTF::Tensor<Complex> and atrip::Atrip::run<Complex> is called:
+// element e of a complex tensor is (synth(2e), synth(2e+1)), the epsilons are (synth(e), 0).
 #include <cinttypes>
 #include <cstdio>
 #include <cstdlib>
@@ -20,9 +22,58 @@ static CTF::Tensor<double> *make(CTF::World &w, std::vector<int> lens, int tenso
   return t;
 }
 
+static CTF::Tensor<atrip::Complex> *make_z(CTF::World &w, std::vector<int> lens, int tensor_id, uint64_t seed,
+                                           double scale) {
+  std::vector<int> syms(lens.size(), NS);
+  auto *t = new CTF::Tensor<atrip::Complex>((int)lens.size(), lens.data(), syms.data(), w);
+  double *d = reinterpret_cast<double *>(t->data);
+  const uint64_t n = (uint64_t)t->size;
+  const bool eps = tensor_id <= 1;
+  if (atrip_b200_synth_to_host(0, seed, tensor_id, scale, 0, eps ? n : 2 * n, d) != 0) {
+    std::fprintf(stderr, "synth failed: %s\n", atrip_b200_last_error());
+    std::exit(2);
+  }
+  if (eps)  // n real values were written to the front: spread them to (value, 0) pairs
+    for (uint64_t e = n; e-- > 0;) {
+      d[2 * e] = d[e];
+      d[2 * e + 1] = 0.0;
+    }
+  return t;
+}
+
+template <typename F, typename Make>
+static int go(CTF::World &world, Make mk, int No, int Nv, uint64_t seed, double scale, size_t max_it, bool naive,
+              bool cT) {
+  using In = atrip::Atrip::Input<F>;
+  auto in = In()
+                .with_epsilon_i(mk(world, {No}, 0, seed, scale))
+                .with_epsilon_a(mk(world, {Nv}, 1, seed, scale))
+                .with_Tai(mk(world, {Nv, No}, 2, seed, scale))
+                .with_Tabij(mk(world, {Nv, Nv, No, No}, 3, seed, scale))
+                .with_Vabij(mk(world, {Nv, Nv, No, No}, 4, seed, scale))
+                .with_Vijka(mk(world, {No, No, No, Nv}, 5, seed, scale))
+                .with_Vabci(mk(world, {Nv, Nv, Nv, No}, 6, seed, scale))
+                .with_Jijka(cT ? mk(world, {No, No, No, Nv}, 7, seed, scale) : nullptr)
+                .with_Jabci(cT ? mk(world, {Nv, Nv, Nv, No}, 8, seed, scale) : nullptr)
+                .with_delete_Vppph(true)
+                .with_tuples_distribution(naive ? In::NAIVE : In::GROUP_AND_SORT)
+                .with_max_iterations(max_it)
+                .with_read_checkpoint_if_exists(false)
+                .with_writeCheckpoint(false)
+                .with_percentage_mod(25);
+  try {
+    auto out = atrip::Atrip::run<F>(in);
+    std::printf("RESULT energy %a %.17g ct_energy %a %.17g\n", out.energy, out.energy, out.ct_energy, out.ct_energy);
+  } catch (std::string const &m) {
+    std::printf("Atrip throwed with msg: %s\n", m.c_str());
+    return 1;
+  }
+  return 0;
+}
+
 int main(int argc, char **argv) {
   if (argc < 5) {
-    std::fprintf(stderr, "usage: %s No Nv seed scale [max_iterations] [group|naive] [cT]\n", argv[0]);
+    std::fprintf(stderr, "usage: %s No Nv seed scale [max_iterations] [group|naive] [cT|T] [complex]\n", argv[0]);
     return 2;
   }
   const int No = std::atoi(argv[1]), Nv = std::atoi(argv[2]);
@@ -34,30 +85,10 @@ int main(int argc, char **argv) {
   MPI_Init(&argc, &argv);
   CTF::World world(argc, argv);
   atrip::Atrip::init(world.comm);
-  using In = atrip::Atrip::Input<double>;
-  auto in = In()
-                .with_epsilon_i(make(world, {No}, 0, seed, scale))
-                .with_epsilon_a(make(world, {Nv}, 1, seed, scale))
-                .with_Tai(make(world, {Nv, No}, 2, seed, scale))
-                .with_Tabij(make(world, {Nv, Nv, No, No}, 3, seed, scale))
-                .with_Vabij(make(world, {Nv, Nv, No, No}, 4, seed, scale))
-                .with_Vijka(make(world, {No, No, No, Nv}, 5, seed, scale))
-                .with_Vabci(make(world, {Nv, Nv, Nv, No}, 6, seed, scale))
-                .with_Jijka(cT ? make(world, {No, No, No, Nv}, 7, seed, scale) : nullptr)
-                .with_Jabci(cT ? make(world, {Nv, Nv, Nv, No}, 8, seed, scale) : nullptr)
-                .with_delete_Vppph(true)
-                .with_tuples_distribution(naive ? In::NAIVE : In::GROUP_AND_SORT)
-                .with_max_iterations(max_it)
-                .with_read_checkpoint_if_exists(false)
-                .with_writeCheckpoint(false)
-                .with_percentage_mod(25);
-  try {
-    auto out = atrip::Atrip::run<double>(in);
-    std::printf("RESULT energy %a %.17g ct_energy %a %.17g\n", out.energy, out.energy, out.ct_energy, out.ct_energy);
-  } catch (std::string const &m) {
-    std::printf("Atrip throwed with msg: %s\n", m.c_str());
-    return 1;
-  }
+  const bool cplx = argc > 8 && !std::strcmp(argv[8], "complex");
+  const int rc = cplx ? go<atrip::Complex>(world, make_z, No, Nv, seed, scale, max_it, naive, cT)
+                      : go<double>(world, make, No, Nv, seed, scale, max_it, naive, cT);
+  if (rc) return rc;
   MPI_Finalize();
   return 0;
 }

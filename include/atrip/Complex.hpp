@@ -1,5 +1,5 @@
-// Complex scalar type of the public API (reference src/atrip/Complex.hpp:16-52).  The B200 engine
-// computes the FP64 real case only (BASELINE.json north_star); run<Complex> throws.
+// Complex scalar type of the public API (reference src/atrip/Complex.hpp:16-52).  Atrip::run is
+// instantiated for double and Complex, as in the reference (Atrip.cxx:1135-1136).
 #pragma once
 #include <complex>
 #include <type_traits>

@@ -10,8 +10,9 @@
  *   - every function returns 0 on success, non-zero on failure; the message is available from
  *     atrip_b200_last_error() (thread-local).  The C++ host turns a non-zero status into a
  *     thrown std::string, which is what the reference throws (Acc.hpp:16-41).
- *   - all tensors are FP64, column-major (first index fastest), exactly the layout CTF
- *     read_all / slice hands to the reference.
+ *   - all tensors are FP64 (real, or complex when atrip_b200_config.field = 1), column-major
+ *     (first index fastest), exactly the layout CTF read_all / slice hands to the reference
+ *     (SURVEY.md Appendix A.1).
  *   - one context drives one GPU; one process per GPU.  There is NO CPU fallback: every entry
  *     point that computes fails if the CUDA device is not usable.
  */
@@ -41,6 +42,11 @@ typedef struct atrip_b200_config {
                            pulls over NVLink by the copy engines (cudaMemcpyAsync from the owner's
                            store, mapped through CUDA IPC): no SM is taken from the contraction and
                            the owner does not take part */
+  int32_t field;        /* 0: F = double (Atrip::run<double>, Atrip.cxx:1135); 1: F = std::complex<double>
+                           (Atrip::run<Complex>, Atrip.cxx:1136).  With field = 1 EVERY tensor pointer of
+                           this API (set_epsilon, set_Tai, load_*, tuple_debug cubes, read_slice) is an
+                           array of interleaved (re, im) doubles = std::complex<double> memory layout,
+                           still declared `double *`; energies stay real (Equations.cxx:176-178) */
 } atrip_b200_config;
 
 /* ---- lifecycle (replaces the ACC set-up in Atrip::run, Atrip.cxx:78-171, 217-218, 364-380) */
@@ -121,6 +127,11 @@ int atrip_b200_allreduce(atrip_b200_ctx *ctx, double *vals, int32_t n);
 /*      slice traffic of the last run on this rank: out[0] = bytes received, out[1] = messages */
 int atrip_b200_last_exchange(const atrip_b200_ctx *ctx, double *out2);
 
+/* ---- debug: order-independent checksum (integer sum of the bit patterns) of the class cubes the
+ *      contraction kernel wrote for the LAST batch of the last run -- separates "contraction output
+ *      changed" from "reduction changed" when chasing run-to-run differences */
+int atrip_b200_debug_cubes_checksum(atrip_b200_ctx *ctx, uint64_t *out);
+
 /* ---- timing of the last atrip_b200_run, measured with CUDA events on the engine's stream:
  *      out[0] = total ms, out[1] = contraction kernel ms, out[2] = reduction kernel ms,
  *      out[3] = number of contraction launches, out[4] = number of reduction launches,
@@ -129,7 +140,7 @@ int atrip_b200_last_timing(const atrip_b200_ctx *ctx, double *out6);
 
 /* ---- derived constants the caller needs for reporting */
 int64_t atrip_b200_kp(const atrip_b200_ctx *ctx);            /* padded contraction length */
-double atrip_b200_flops_per_tuple(const atrip_b200_ctx *ctx); /* 12 No^3 (No+Nv), Atrip.cxx:578-580 */
+double atrip_b200_flops_per_tuple(const atrip_b200_ctx *ctx); /* 12 No^3 (No+Nv), x4 complex; Atrip.cxx:578-580 */
 int64_t atrip_b200_batch_tuples(const atrip_b200_ctx *ctx);  /* tuples per contraction launch */
 
 /* ---- measurement helpers
@@ -180,6 +191,20 @@ int64_t atrip_b200_host_plan_batch(int64_t Nv, int32_t rank, int32_t nranks, con
 /*      cache slots per store that any window of `batch` consecutive tuples of the list needs */
 int atrip_b200_host_cache_need(int64_t Nv, int32_t rank, int32_t nranks, const uint64_t *abc, int64_t n,
                                int64_t batch, int64_t *out3);
+
+/* ---- complex field, host-only checks of the device code's shared __host__ __device__ pieces
+ *      (CPU test-suite hooks; no device needed).
+ *      atrip_b200_host_store_source: which source-tensor element a store element of the complex
+ *      layout holds (stores.cuh "complex field").  store 0 = AX (a = variant, x = virtual index,
+ *      row = p + q No), store 1 = BY (a = transposed-diagonal flag, x,y = ordered pair, row = r).
+ *      out[0] = tensor (0 padding, 1 Tabij, 2 Vijka, 3 Vabci), out[1] = part (0 re, 1 im),
+ *      out[2] = sign, out[3] = column-major element index in that tensor.
+ *      atrip_b200_host_energy_z: get_energy_distinct/same<Complex> (Equations.cxx:101-238) over plain
+ *      interleaved-complex No^3 cubes through the per-point function the device kernel uses. */
+int atrip_b200_host_store_source(int32_t store, int64_t No, int64_t Nv, int32_t a, int64_t x, int64_t y,
+                                 int64_t row, int64_t kappa, double *out4);
+double atrip_b200_host_energy_z(int64_t No, double epsabc, const double *eps_i, const double *Tijk,
+                                const double *Zijk, int32_t same);
 
 #ifdef __cplusplus
 }

@@ -4,6 +4,7 @@ import os
 import re
 
 import numpy as np
+import pytest
 
 from atrip_b200 import capi
 
@@ -84,3 +85,17 @@ def test_slice_owner_matches_rankmap(lib, oracle):
                 want = oracle.L.oracle_owner_pair(x, y, Nv, n) if Nv % n == 0 else x % n
                 assert capi.slice_owner(capi.VABCI, x, y, Nv, n) == want
                 assert capi.slice_owner(capi.TABIJ, x, y, Nv, n) == want
+
+
+def test_ring_release_is_ordered_after_all_dmmas_in_sass(lib):
+    """every contract_kernel instantiation hands a TMA ring stage back only after all DMMAs that
+    consume its fragment loads (tools/check_sass_order.py; profiles/r01_ring_release_race.txt)"""
+    import shutil
+    import sys
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not on PATH")
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import check_sass_order
+    from atrip_b200 import capi
+    seen, bad = check_sass_order.check(capi.lib_path())
+    assert seen >= 30 and not bad, bad

@@ -1,0 +1,51 @@
+"""Checks the consumer-side release of the contraction kernel's TMA ring in the compiled SASS.
+
+A consumer warp may hand a ring stage back to the producer (mbarrier arrive on the stage's "empty"
+barrier, SASS `SYNCS.ARRIVE.TRANS64.A1T0`) only after every LDS of that stage has delivered its data.
+The source orders  fragment loads + DMMAs -> __syncwarp() -> arrive,  but ptxas is free to move the
+arrive (no register dependency) and the WARPSYNC inside a basic block: in a straight-line loop body it
+placed the arrive between the last LDS and the DMMAs that consume them, and the kernel then produced
+run-to-run different cubes (profiles/r01_ring_release_race.txt).  In-order issue makes the arrive safe
+iff all DMMAs of the stage (which wait for their LDS operands at issue) precede it.  This script
+asserts exactly that for every contract_kernel instantiation:  last DMMA < WARPSYNC < arrive.
+
+  python tools/check_sass_order.py [path/to/libatrip_b200.so]      exit code 1 on a violation
+"""
+import os
+import re
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def check(lib):
+    out = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
+    bad, seen = [], 0
+    for chunk in out.split("Function : ")[1:]:
+        name = chunk.split("\n", 1)[0].strip()
+        if "contract_kernel" not in name:
+            continue
+        seen += 1
+        ins = [l for l in chunk.split("\n") if re.search(r"/\*[0-9a-f]{4,}\*/\s+\S", l)]
+        arrive = [i for i, l in enumerate(ins) if "SYNCS.ARRIVE.TRANS64.A1T0" in l]
+        dmma = [i for i, l in enumerate(ins) if "DMMA" in l]
+        lds = [i for i, l in enumerate(ins) if re.search(r"\bLDS", l)]
+        wsync = [i for i, l in enumerate(ins) if "WARPSYNC" in l]
+        ok = len(arrive) == 1 and dmma and lds
+        if ok:
+            a = arrive[0]
+            before = [w for w in wsync if w < a]
+            ok = max(dmma) < a and max(lds) < a and bool(before) and max(before) > max(dmma) and max(before) > max(lds)
+        if not ok:
+            bad.append(name)
+    return seen, bad
+
+
+if __name__ == "__main__":
+    lib = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "atrip_b200", "csrc", "libatrip_b200.so")
+    seen, bad = check(lib)
+    print(f"{seen} contract_kernel instantiations checked, {len(bad)} with the stage release not after all DMMAs")
+    for b in bad:
+        print("  VIOLATION:", b)
+    sys.exit(1 if bad or not seen else 0)
