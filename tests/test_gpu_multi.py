@@ -19,9 +19,10 @@ def _worker(rank, world, q_id, q_out, case):
     sys.path.insert(0, ROOT)
     import atrip_b200
     from atrip_b200 import capi
-    No, Nv, seed, scale, with_J, batch, host_tensors, debug, transport = case
+    No, Nv, seed, scale, with_J, batch, host_tensors, debug, transport = case[:9]
+    field = case[9] if len(case) > 9 else 0
     eng = atrip_b200.Engine(No, Nv, device=rank, rank=rank, nranks=world, with_J=with_J, batch_tuples=batch,
-                            resident=False, transport=transport)
+                            resident=False, transport=transport, field=field)
     if rank == 0:
         uid = capi.comm_unique_id()
         for _ in range(world - 1):
@@ -85,6 +86,19 @@ def test_sharded_runs_match_reference_vectors(oracle, golden, world, transport):
             ref_ct = fh(r["ct_energy"])
             assert abs(-ct - ref_ct) <= E_ABS and abs(-ct - ref_ct) <= 1e-11 * max(abs(ref_ct), abs(e))
             assert xb > 0, "no slices travelled: the sharded path was not exercised"
+
+
+@pytest.mark.parametrize("transport", [1, 2], ids=["nccl", "p2p"])
+def test_sharded_complex_runs_match_reference_vectors(golden, transport):
+    """F = Complex with sharded stores: a complex AX slice carries both K-doubled variants and travels
+    as one slice; whole-run energies of the reference's run<Complex> incl. (cT) on 2 GPUs"""
+    for r in [golden["complex_runs"][i] for i in (1, 2)]:
+        res = run_case(2, (r["No"], r["Nv"], r["seed"], r["scale"], r["with_J"], 37, None, [], transport, 1))
+        for rank, e, ct, xb, _ in res:
+            assert abs(-e - fh(r["energy"])) <= E_ABS and abs(-e - fh(r["energy"])) <= E_REL * abs(e), (r, rank, -e)
+            ref_ct = fh(r["ct_energy"])
+            assert abs(-ct - ref_ct) <= E_ABS and abs(-ct - ref_ct) <= 1e-11 * max(abs(ref_ct), abs(e))
+            assert xb > 0
 
 
 @pytest.mark.parametrize("transport", [1, 2], ids=["nccl", "p2p"])

@@ -192,6 +192,27 @@ def test_determinism_and_bench_size_properties(ab):
     eng.close()
 
 
+@pytest.mark.parametrize("No,Nv,field", [(16, 48, 0), (16, 24, 1), (8, 24, 0), (24, 40, 1), (64, 64, 0)])
+def test_repeated_runs_are_bit_identical_without_k_padding(ab, No, Nv, field):
+    """regression for the ring-release race (profiles/r01_ring_release_race.txt): shapes whose
+    contraction length has NO zero padding ((No+Nv) % 16 == 0; real and complex field) used a
+    straight-line loop body in which ptxas handed ring stages back before their last fragment loads
+    had landed -- run-to-run different cubes in ~1 of 10 large launches.  Same batch, many times:
+    energies and the integer checksum of the class cubes must be identical every time."""
+    from atrip_b200 import capi
+    eng = ab.Engine(No, Nv, field=field)
+    assert eng.kp == (2 if field else 1) * (No + Nv)
+    eng.fill_synthetic(5, 0.01)
+    n = eng.build_tuples(capi.GROUP_AND_SORT)
+    cnt = min(n, eng.batch_tuples)
+    seen = set()
+    for _ in range(25 if No < 64 else 8):
+        e, _ = eng.run(0, cnt)
+        seen.add((e, eng.cubes_checksum()))
+    eng.close()
+    assert len(seen) == 1, seen
+
+
 def test_bench_size_tuples_vs_oracle(ab, oracle):
     """a few tuples at the bench size against the oracle's per-tuple path fed slice by slice
     (the full tensors would be 25 GB on the host: the oracle is given synthetic slices)"""
