@@ -206,6 +206,9 @@ def main():
                     help="N>1: every GPU holds a full replica of the stores (no slice exchange)")
     ap.add_argument("--transport", type=int, default=0, choices=[0, 1, 2],
                     help="N>1 slice exchange: 1 NCCL send/recv, 2 P2P copy-engine pulls, 0 engine default")
+    ap.add_argument("--field", default="real", choices=["real", "complex"],
+                    help="complex: Atrip::run<Complex> instantiation (4x the FLOPs per tuple, Atrip.cxx:578-580); "
+                         "device-resident synthetic stores only (no e2e / CPU legs)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
@@ -214,8 +217,11 @@ def main():
     cfg = dict(CONFIGS[args.config], name=args.config)
     if args.tuples_per_step:
         cfg["tuples_per_step"] = args.tuples_per_step
-    if cfg.get("no_e2e"):
+    if cfg.get("no_e2e") or args.field == "complex":
         args.no_e2e = True
+    if args.field == "complex":
+        args.no_cpu = True
+        assert args.impl == "ours", "the reference arm times the real (double) instantiation"
     assert args.impl == "reference" or args.gpus >= cfg.get("min_gpus", 1), \
         f"{args.config} needs at least {cfg.get('min_gpus')} GPUs (stores are sharded over the ranks)"
     if args.impl == "reference":
@@ -255,7 +261,8 @@ def main():
     # batch from its peers with ncclSend/ncclRecv on a side stream, one batch ahead of the compute
     sharded = world > 1 and not args.replicate
     eng = atrip_b200.Engine(No, Nv, device=local, rank=rank, nranks=world, resident=not sharded,
-                            transport=args.transport)
+                            transport=args.transport,
+                            field=capi.FIELD_COMPLEX if args.field == "complex" else capi.FIELD_REAL)
     if world > 1:  # the engine's own NCCL communicator; its 128-byte id travels over torch.distributed
         box = [capi.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(box, src=0)
@@ -370,8 +377,9 @@ def main():
         line = {
             "metric": "(T) FP64 TFLOP/s", "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": cfg["name"] + ": " + cfg["desc"], "No": No, "Nv": Nv, "tuples_per_step": tps,
+            "dtype": "c128" if args.field == "complex" else "f64", "data": "synthetic",
+            "config": {"workload": cfg["name"] + ": " + cfg["desc"] + (" [complex field]" if args.field == "complex" else ""),
+                       "No": No, "Nv": Nv, "tuples_per_step": tps,
                        "tuples_per_step_all_ranks": tps * world, "distribution": "group_and_sort (GPU == node)",
                        "stores": ("sharded: owned slices + fetch cache prefetched one batch ahead on a side stream, "
                                   + {0: "engine default transport", 1: "ncclSend/ncclRecv",

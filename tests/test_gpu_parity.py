@@ -213,16 +213,20 @@ def test_repeated_runs_are_bit_identical_without_k_padding(ab, No, Nv, field):
     assert len(seen) == 1, seen
 
 
-def test_bench_size_tuples_vs_oracle(ab, oracle):
+@pytest.mark.parametrize("No,Nv,tuples", [
+    (40, 400, [(3, 57, 399), (11, 11, 200)]),      # c2, the N=1 bench workload (padded K, 5x5 plan)
+    (64, 192, [(5, 64, 191), (100, 100, 101)]),    # the c3 plan (4x8 fragments) with UNPADDED K = 256
+])
+def test_bench_size_tuples_vs_oracle(ab, oracle, No, Nv, tuples):
     """a few tuples at the bench size against the oracle's per-tuple path fed slice by slice
     (the full tensors would be 25 GB on the host: the oracle is given synthetic slices)"""
-    No, Nv, seed, scale = 40, 400, 12345, 0.1
+    seed, scale = 12345, 0.1
     eng = ab.Engine(No, Nv)
     eng.fill_synthetic(seed, scale)
     epsi, epsa = oracle.fill(seed, EPS_I, scale, No), oracle.fill(seed, EPS_A, scale, Nv)
     tai = oracle.fill(seed, TAI, scale, No * Nv)
 
-    for abc in [(3, 57, 399), (11, 11, 200)]:
+    for abc in tuples:
         a, b, c = abc
         S = oracle.synth_tuple_slices(No, Nv, abc, seed=seed, scale=scale)
         T = oracle.doubles(No, Nv, S)
