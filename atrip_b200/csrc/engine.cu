@@ -155,6 +155,20 @@ T *dalloc(size_t n) {
   return p;
 }
 
+// scratch device buffer of one call: freed on every exit path, including a thrown Fail
+template <typename T>
+struct Scratch {
+  T *p = nullptr;
+  Scratch() = default;
+  explicit Scratch(size_t n) : p(dalloc<T>(n)) {}
+  Scratch(const Scratch &) = delete;
+  Scratch &operator=(const Scratch &) = delete;
+  void alloc(size_t n) { p = dalloc<T>(n); }
+  ~Scratch() {
+    if (p) cudaFree(p);
+  }
+};
+
 }  // namespace
 
 constexpr int REC_RING = 4;  // batches the host may run ahead of the device
@@ -1052,9 +1066,10 @@ void tuple_debug_impl(atrip_b200_ctx *c, int64_t a, int64_t b, int64_t cc, doubl
   const uint64_t slot = c->rec_uses % REC_RING;  // the ring slot run_list is about to use
   run_list(c, &one, 1, &e, nullptr);
   const size_t cube = (size_t)c->No * c->No * c->No, cd = esz(c) * cube;  // complex: interleaved cubes
-  double *dT = nullptr, *dZ = nullptr;
-  if (Tijk) dT = dalloc<double>(cd);
-  if (Zijk) dZ = dalloc<double>(cd);
+  Scratch<double> sT, sZ;
+  if (Tijk) sT.alloc(cd);
+  if (Zijk) sZ.alloc(cd);
+  double *dT = sT.p, *dZ = sZ.p;
   if (Tijk || Zijk) {
     ReduceParams P = reduce_params(c, c->d_recs + slot * c->batch, 1, false, 0);
     if (c->cplx) cubes_z_kernel<<<grid_for(cube, c->nsm), 256, 0, c->stream>>>(P, 0, dT, dZ);
@@ -1064,8 +1079,6 @@ void tuple_debug_impl(atrip_b200_ctx *c, int64_t a, int64_t b, int64_t cc, doubl
   if (Tijk) CUDA_OK(cudaMemcpyAsync(Tijk, dT, cd * 8, cudaMemcpyDeviceToHost, c->stream));
   if (Zijk) CUDA_OK(cudaMemcpyAsync(Zijk, dZ, cd * 8, cudaMemcpyDeviceToHost, c->stream));
   CUDA_OK(cudaStreamSynchronize(c->stream));
-  if (dT) cudaFree(dT);
-  if (dZ) cudaFree(dZ);
   if (energy) *energy = e;
 }
 
@@ -1095,13 +1108,13 @@ void read_slice_impl(atrip_b200_ctx *c, int kind, int64_t x, int64_t y, double *
     throw Fail{"unknown slice kind"};
   }
   if (kind == 201) REQUIRE(y >= 0 && y < (int64_t)Nv, "slice index y out of range");
-  double *d = dalloc<double>(esz(c) * n);
+  Scratch<double> sd(esz(c) * n);
+  double *d = sd.p;
   if (c->cplx) read_slice_z_kernel<<<grid_for(n, c->nsm), 256, 0, c->stream>>>(kind, dims_of(c), ax, by, vij, (int)y, d);
   else read_slice_kernel<<<grid_for(n, c->nsm), 256, 0, c->stream>>>(kind, dims_of(c), ax, by, vij, (int)y, d);
   CUDA_OK(cudaGetLastError());
   CUDA_OK(cudaMemcpyAsync(out, d, esz(c) * n * 8, cudaMemcpyDeviceToHost, c->stream));
   CUDA_OK(cudaStreamSynchronize(c->stream));
-  cudaFree(d);
 }
 
 void comm_init_impl(atrip_b200_ctx *c, const void *id128) {
@@ -1121,7 +1134,8 @@ void comm_init_impl(atrip_b200_ctx *c, const void *id128) {
   std::vector<cudaIpcMemHandle_t> all((size_t)n * 5);
   for (int k = 0; k < nh; k++) CUDA_OK(cudaIpcGetMemHandle(&all[(size_t)me * 5 + k], mine[k]));
   const size_t per = 5 * sizeof(cudaIpcMemHandle_t);
-  unsigned char *d = dalloc<unsigned char>(per * n);
+  Scratch<unsigned char> sd(per * n);
+  unsigned char *d = sd.p;
   CUDA_OK(cudaMemcpyAsync(d + per * me, &all[(size_t)me * 5], per, cudaMemcpyHostToDevice, c->stream));
   NCCL_OK(N.GroupStart());
   for (int p = 0; p < n; p++) {
@@ -1132,7 +1146,6 @@ void comm_init_impl(atrip_b200_ctx *c, const void *id128) {
   NCCL_OK(N.GroupEnd());
   CUDA_OK(cudaMemcpyAsync(all.data(), d, per * n, cudaMemcpyDeviceToHost, c->stream));
   CUDA_OK(cudaStreamSynchronize(c->stream));
-  cudaFree(d);
   for (int k = 0; k < 5; k++) c->peer[k].assign((size_t)n, nullptr);
   for (int p = 0; p < n; p++)
     for (int k = 0; k < nh; k++) {
@@ -1315,7 +1328,8 @@ int atrip_b200_read_slice(atrip_b200_ctx *c, int32_t kind, int64_t x, int64_t y,
 }
 int atrip_b200_debug_cubes_checksum(atrip_b200_ctx *c, uint64_t *out) {
   return guarded(c, [&] {
-    unsigned long long *d = dalloc<unsigned long long>(1);
+    Scratch<unsigned long long> sd(1);
+    unsigned long long *d = sd.p;
     CUDA_OK(cudaMemsetAsync(d, 0, 8, c->stream));
     const size_t n = (size_t)c->last_nt * ncubes(c) * cube_blocked_elems(c->No);
     if (n) checksum_kernel<<<1024, 256, 0, c->stream>>>(c->R[c->last_buf], n, d);
@@ -1323,7 +1337,6 @@ int atrip_b200_debug_cubes_checksum(atrip_b200_ctx *c, uint64_t *out) {
     unsigned long long h = 0;
     CUDA_OK(cudaMemcpyAsync(&h, d, 8, cudaMemcpyDeviceToHost, c->stream));
     CUDA_OK(cudaStreamSynchronize(c->stream));
-    cudaFree(d);
     *out = h;
   });
 }
@@ -1365,7 +1378,8 @@ int atrip_b200_measure_dmma_peak(int32_t device, double *tflops) {
     cudaDeviceProp prop;
     CUDA_OK(cudaGetDeviceProperties(&prop, device));
     const int grid = prop.multiProcessorCount * 2, threads = 256, iters = 40000;
-    double *out = dalloc<double>((size_t)grid * threads);
+    Scratch<double> sout((size_t)grid * threads);
+    double *out = sout.p;
     cudaEvent_t e0, e1;
     CUDA_OK(cudaEventCreate(&e0));
     CUDA_OK(cudaEventCreate(&e1));
@@ -1383,7 +1397,6 @@ int atrip_b200_measure_dmma_peak(int32_t device, double *tflops) {
     CUDA_OK(cudaGetLastError());
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
-    cudaFree(out);
     *tflops = best;
   });
 }
@@ -1393,14 +1406,14 @@ int atrip_b200_synth_to_host(int32_t device, uint64_t seed, int32_t tensor_id, d
   return guarded(nullptr, [&] {
     CUDA_OK(cudaSetDevice(device));
     const uint64_t chunk = 1ull << 26;  // 512 MiB
-    double *d = dalloc<double>(std::min<uint64_t>(chunk, std::max<uint64_t>(count, 1)));
+    Scratch<double> sd(std::min<uint64_t>(chunk, std::max<uint64_t>(count, 1)));
+    double *d = sd.p;
     for (uint64_t off = 0; off < count; off += chunk) {
       const uint64_t n = std::min(chunk, count - off);
       synth_range_kernel<<<2048, 256>>>(d, synth_key(seed, tensor_id), tensor_id, scale, first + off, n);
       CUDA_OK(cudaGetLastError());
       CUDA_OK(cudaMemcpy(host + off, d, n * sizeof(double), cudaMemcpyDeviceToHost));
     }
-    cudaFree(d);
   });
 }
 
