@@ -99,3 +99,28 @@ def test_ring_release_is_ordered_after_all_dmmas_in_sass(lib):
     from atrip_b200 import capi
     seen, bad = check_sass_order.check(capi.lib_path())
     assert seen >= 30 and not bad, bad
+
+
+def test_contraction_plan_is_valid_for_every_No(lib):
+    """the tile planner (engine.cu: plan_contraction, exposed as atrip_b200_host_plan) must return
+    a launchable plan for every supported No: the row tile fits the rows a stage reserves and the
+    TMA box limits (<= 256 per dimension), the ring fits the 227 KB of shared memory with at least
+    three stages, and the tiles cover the whole No^2 x No class matrix"""
+    variants = set()
+    for No in range(1, 257):
+        p = capi.host_plan(No)
+        MI, NI, nw, tu, tv = p["MI"], p["NI"], p["warps"], p["tu"], p["tv"]
+        assert p["arows"] == nw * MI * 8 and tu * tv <= p["arows"], (No, p)
+        assert 1 <= tu <= min(No, 256) and 1 <= tv <= min(No, 256), (No, p)
+        utiles, vtiles = -(-No // tu), -(-No // tv)
+        assert p["row_tiles"] == utiles * vtiles and p["col_tiles"] * NI * 8 >= No, (No, p)
+        assert 3 <= p["stages"] <= 12 and p["smem"] <= 232448, (No, p)
+        assert p["smem"] == p["stages"] * (p["arows"] + NI * 8) * 128 + 1024, (No, p)
+        assert 4 <= nw and (nw + 1) * 32 <= 512 and 0.0 < p["useful"] <= 1.0 + 1e-9, (No, p)
+        variants.add((MI, NI))
+    assert len(variants) >= 10  # the planner really uses the compiled family
+    # the bench configs keep the plans the measurements in profiles/ were taken with
+    assert [(capi.host_plan(n)["MI"], capi.host_plan(n)["NI"]) for n in (40, 64, 100, 32)] == \
+        [(5, 5), (4, 8), (2, 13), (4, 4)]
+    with pytest.raises(capi.EngineError):
+        capi.host_plan(257)
