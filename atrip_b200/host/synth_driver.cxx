@@ -61,6 +61,15 @@ static int go(CTF::World &world, Make mk, int No, int Nv, uint64_t seed, double 
                 .with_read_checkpoint_if_exists(false)
                 .with_writeCheckpoint(false)
                 .with_percentage_mod(25);
+  // SYNTH_CHECKPOINT=<path> [SYNTH_CHECKPOINT_EVERY=<iterations>]: write checkpoints and resume from <path>
+  // if it exists (Atrip.cxx:586-621, 713-731)
+  if (const char *ck = std::getenv("SYNTH_CHECKPOINT")) {
+    const char *ev = std::getenv("SYNTH_CHECKPOINT_EVERY");
+    in.with_checkpoint_path(ck)
+        .with_read_checkpoint_if_exists(true)
+        .with_writeCheckpoint(true)
+        .with_checkpoint_at_every_iteration(ev ? std::strtoull(ev, nullptr, 10) : 10);
+  }
   try {
     auto out = atrip::Atrip::run<F>(in);
     std::printf("RESULT energy %a %.17g ct_energy %a %.17g\n", out.energy, out.energy, out.ct_energy, out.ct_energy);
