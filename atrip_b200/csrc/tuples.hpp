@@ -1,10 +1,10 @@
 // Host-side tuple lists of the engine (no CUDA here; unit-tested on CPU).
 //
 // Replaces TuplesDistribution::get_tuples (reference Tuples.cxx:89-141, 156-407) with one GPU per
-// "node".  Unlike the reference, no rank materialises the O(Nv^3) global list: the distribution
-// is computed in two streaming passes over the enumeration (container sizes, then this rank's
-// share), which yields exactly the reference's lists (tests/test_tuples.py compares them with the
-// reference's own special_distribution).
+// "node".  Unlike the reference, no rank materialises (or even walks) the O(Nv^3) global list: the
+// container sizes are closed-form per residue class and a rank only visits the tuples that can be
+// its own (see group_and_sort_tuples), which yields exactly the reference's lists (tests/test_host.py
+// compares them with the reference's own special_distribution).
 #pragma once
 #include <algorithm>
 #include <array>
@@ -75,16 +75,44 @@ inline bool takes(const Key &k, uint64_t me, uint64_t pos, uint64_t sz) {
 
 // GROUP_AND_SORT for node `me` of `n` (Tuples.cxx:156-308), padded with FAKE to the longest
 // node's list (Tuples.cxx:346-377).  If counts != nullptr it receives every node's real count.
+//
+// The reference walks the whole O(Nv^3) enumeration on every node leader.  Here
+//   * the container sizes come from residue-class counts (O(Nv^2 n) instead of O(Nv^3)): for a
+//     pair (a,b) the c's of each residue class form an arithmetic progression whose length is
+//     closed-form;
+//   * the second pass visits only the tuples that have an index congruent to `me` -- a node only
+//     ever takes from containers whose node set contains it, and every tuple of such a container
+//     has such an index -- in the reference's lexicographic order, so the positions inside the
+//     containers (which decide the halves / thirds) are the reference's: (a,b) pairs with a home
+//     index walk all c, the others only c = me (mod n);
+//   * the sort runs on packed 64-bit keys (21 bits per index).
+// The lists are the reference's, tuple for tuple (tests/test_host.py compares hashes with the
+// reference's own special_distribution and with the oracle).
 inline std::vector<Tuple> group_and_sort_tuples(uint64_t Nv, uint64_t me, uint64_t n, bool pad = true,
                                                 std::vector<uint64_t> *counts = nullptr) {
   const uint64_t nkeys = n * n * n;
+  // key of every residue triple (ra, rb, rc)
+  std::vector<gs::Key> keys(nkeys);
+  std::vector<uint32_t> kid(nkeys);
+  for (uint64_t ra = 0; ra < n; ra++)
+    for (uint64_t rb = 0; rb < n; rb++)
+      for (uint64_t rc = 0; rc < n; rc++) {
+        const gs::Key k = gs::key_of(ra, rb, rc, n);
+        keys[(ra * n + rb) * n + rc] = k;
+        kid[(ra * n + rb) * n + rc] = (uint32_t)k.id(n);
+      }
+  // number of c in [lo, Nv) with c % n == r
+  auto count_c = [&](uint64_t lo, uint64_t r) -> uint64_t {
+    const uint64_t first = lo + (r + n - lo % n) % n;
+    return first < Nv ? (Nv - 1 - first) / n + 1 : 0;
+  };
   std::vector<uint64_t> size(nkeys, 0), seen(nkeys, 0);
   for (uint64_t a = 0; a < Nv; a++)
-    for (uint64_t b = a; b < Nv; b++)
-      for (uint64_t c = b; c < Nv; c++) {
-        if (a == b && b == c) continue;
-        size[gs::key_of(a, b, c, n).id(n)]++;
-      }
+    for (uint64_t b = a; b < Nv; b++) {
+      const uint64_t lo = b + (a == b ? 1 : 0);  // a == b == c is not a tuple
+      const uint64_t base = ((a % n) * n + b % n) * n;
+      for (uint64_t r = 0; r < n; r++) size[kid[base + r]] += count_c(lo, r);
+    }
   // every node's count follows from the container sizes alone
   std::vector<uint64_t> cnt(n, 0);
   for (uint64_t x = 0; x < n; x++) {
@@ -102,26 +130,37 @@ inline std::vector<Tuple> group_and_sort_tuples(uint64_t Nv, uint64_t me, uint64
     }
   }
   if (counts) *counts = cnt;
-  std::vector<Tuple> mine;
-  mine.reserve(cnt[me]);
-  for (uint64_t a = 0; a < Nv; a++)
-    for (uint64_t b = a; b < Nv; b++)
-      for (uint64_t c = b; c < Nv; c++) {
-        if (a == b && b == c) continue;
-        const gs::Key k = gs::key_of(a, b, c, n);
-        const uint64_t id = k.id(n), pos = seen[id]++;
-        if (gs::takes(k, me, pos, size[id])) mine.push_back(Tuple{a, b, c});
-      }
-  // home elements to the back so the non-home indices vary slowest after sorting (:267-286)
-  for (auto &t : mine) {
-    const bool h0 = t[0] % n == me, h1 = t[1] % n == me, h2 = t[2] % n == me;
+  // my share, with the home elements moved to the back so that the non-home indices vary slowest
+  // after sorting (:267-286); packed as t0 << 42 | t1 << 21 | t2 for the sort
+  std::vector<uint64_t> packed;
+  packed.reserve(cnt[me]);
+  auto visit = [&](uint64_t a, uint64_t b, uint64_t c, uint64_t base) {
+    const uint64_t rc = c % n, slot = base + rc, id = kid[slot], pos = seen[id]++;
+    if (!gs::takes(keys[slot], me, pos, size[id])) return;
+    uint64_t t[3] = {a, b, c};
+    const bool h0 = a % n == me, h1 = b % n == me, h2 = rc == me;
     if (h0) {
       if (!h2) std::swap(t[0], t[2]);
       else if (!h1) std::swap(t[0], t[1]);
     } else if (h1 && !h2) std::swap(t[1], t[2]);
+    packed.push_back(t[0] << 42 | t[1] << 21 | t[2]);
+  };
+  for (uint64_t a = 0; a < Nv; a++)
+    for (uint64_t b = a; b < Nv; b++) {
+      const uint64_t lo = b + (a == b ? 1 : 0), base = ((a % n) * n + b % n) * n;
+      if (a % n == me || b % n == me) {
+        for (uint64_t c = lo; c < Nv; c++) visit(a, b, c, base);
+      } else {
+        for (uint64_t c = lo + (me + n - lo % n) % n; c < Nv; c += n) visit(a, b, c, base);
+      }
+    }
+  std::sort(packed.begin(), packed.end());
+  std::vector<Tuple> mine(packed.size());
+  for (size_t i = 0; i < packed.size(); i++) {
+    Tuple t{packed[i] >> 42, (packed[i] >> 21) & 0x1fffff, packed[i] & 0x1fffff};
+    std::sort(t.begin(), t.end());
+    mine[i] = t;
   }
-  std::sort(mine.begin(), mine.end());
-  for (auto &t : mine) std::sort(t.begin(), t.end());
   if (pad) {
     const uint64_t mx = *std::max_element(cnt.begin(), cnt.end());
     mine.resize(mx, Tuple{0, 0, 0});
