@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include "contraction.cuh"
 #include "reduction.cuh"
+#include "reduction_async.cuh"
 #include "reduction_z.cuh"
 #include "schedule.hpp"
 #include "stores.cuh"
@@ -236,6 +237,7 @@ struct atrip_b200_ctx {
 
   double timing[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   int last_nt = 0, last_buf = 0;  // tuples and cube buffer of the last batch run (debug checksum)
+  bool reduce_async = false;      // ATRIP_B200_REDUCE=async: experimental bulk-copy reduction (reduction_async.cuh)
 };
 
 namespace {
@@ -435,6 +437,8 @@ void launch_reduce(atrip_b200_ctx *c, const TupleRec *d_recs, int ntuples, bool 
     const size_t smz = reduce_z_smem_bytes(c->No, ct);
     if (ct) reduce_z_kernel<true><<<grid, REDUCE_THREADS, smz, c->rstream>>>(P);
     else reduce_z_kernel<false><<<grid, REDUCE_THREADS, smz, c->rstream>>>(P);
+  } else if (c->reduce_async && !ct) {
+    reduce_async_kernel<<<grid, REDUCE_THREADS, reduce_async_smem_bytes(c->No), c->rstream>>>(P);
   } else if (ct) reduce_kernel<true><<<grid, REDUCE_THREADS, smem, c->rstream>>>(P);
   else reduce_kernel<false><<<grid, REDUCE_THREADS, smem, c->rstream>>>(P);
   CUDA_OK(cudaGetLastError());
@@ -496,6 +500,10 @@ void create_impl(atrip_b200_ctx *c) {
                                (int)reduce_smem_bytes(c->No, false)));
   CUDA_OK(cudaFuncSetAttribute((const void *)reduce_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)reduce_smem_bytes(c->No, true)));
+  if (const char *e = std::getenv("ATRIP_B200_REDUCE")) c->reduce_async = std::string(e) == "async" && !c->cplx;
+  if (c->reduce_async)
+    CUDA_OK(cudaFuncSetAttribute((const void *)reduce_async_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)reduce_async_smem_bytes(c->No)));
   if (c->cplx) {
     REQUIRE(reduce_z_smem_bytes(c->No, true) <= c->smem_limit, "No too large for the complex reduction kernel");
     CUDA_OK(cudaFuncSetAttribute((const void *)reduce_z_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
