@@ -1447,6 +1447,10 @@ int64_t atrip_b200_host_tuples(int32_t distribution, int64_t Nv, int32_t rank, i
     g_error = "atrip_b200_host_tuples: bad arguments";
     return -1;
   }
+  if (distribution == 1 && (!abc || cap <= 0)) {  // length only: the container census suffices
+    const gs::Census C = gs::census((uint64_t)Nv, (uint64_t)nranks);
+    return (int64_t)(pad ? *std::max_element(C.cnt.begin(), C.cnt.end()) : C.cnt[(size_t)rank]);
+  }
   std::vector<Tuple> t = distribution == 0 ? naive_tuples(Nv, rank, nranks)
                                            : group_and_sort_tuples(Nv, rank, nranks, pad != 0);
   if (distribution == 0 && !pad)

@@ -73,6 +73,63 @@ inline bool takes(const Key &k, uint64_t me, uint64_t pos, uint64_t sz) {
 }
 }  // namespace gs
 
+namespace gs {
+// pass 1 of group-and-sort: container sizes (per sorted node set) and every node's tuple count
+struct Census {
+  std::vector<Key> keys;        // key of every residue triple (ra, rb, rc)
+  std::vector<uint32_t> kid;    // its container id
+  std::vector<uint64_t> size;   // tuples per container
+  std::vector<uint64_t> cnt;    // tuples per node
+};
+inline Census census(uint64_t Nv, uint64_t n) {
+  Census C;
+  const uint64_t nkeys = n * n * n;
+  // key of every residue triple (ra, rb, rc)
+  std::vector<Key> &keys = C.keys;
+  std::vector<uint32_t> &kid = C.kid;
+  keys.resize(nkeys);
+  kid.resize(nkeys);
+  for (uint64_t ra = 0; ra < n; ra++)
+    for (uint64_t rb = 0; rb < n; rb++)
+      for (uint64_t rc = 0; rc < n; rc++) {
+        const Key k = key_of(ra, rb, rc, n);
+        keys[(ra * n + rb) * n + rc] = k;
+        kid[(ra * n + rb) * n + rc] = (uint32_t)k.id(n);
+      }
+  // number of c in [lo, Nv) with c % n == r
+  auto count_c = [&](uint64_t lo, uint64_t r) -> uint64_t {
+    const uint64_t first = lo + (r + n - lo % n) % n;
+    return first < Nv ? (Nv - 1 - first) / n + 1 : 0;
+  };
+  std::vector<uint64_t> &size = C.size;
+  size.assign(nkeys, 0);
+  for (uint64_t a = 0; a < Nv; a++)
+    for (uint64_t b = a; b < Nv; b++) {
+      const uint64_t lo = b + (a == b ? 1 : 0);  // a == b == c is not a tuple
+      const uint64_t base = ((a % n) * n + b % n) * n;
+      for (uint64_t r = 0; r < n; r++) size[kid[base + r]] += count_c(lo, r);
+    }
+  // every node's count follows from the container sizes alone
+  std::vector<uint64_t> &cnt = C.cnt;
+  cnt.assign(n, 0);
+  for (uint64_t x = 0; x < n; x++) {
+    cnt[x] += size[x + x * n + x * n * n];  // one home node: the whole container
+    for (uint64_t y = x + 1; y < n; y++) {
+      const uint64_t s2 = size[x + y * n + y * n * n];  // two home nodes: halves
+      cnt[x] += s2 / 2;
+      cnt[y] += s2 - s2 / 2;
+      for (uint64_t z = y + 1; z < n; z++) {
+        const uint64_t s3 = size[x + y * n + z * n * n];  // three: thirds
+        cnt[x] += s3 / 3;
+        cnt[y] += s3 / 3;
+        cnt[z] += s3 - 2 * (s3 / 3);
+      }
+    }
+  }
+  return C;
+}
+}  // namespace gs
+
 // GROUP_AND_SORT for node `me` of `n` (Tuples.cxx:156-308), padded with FAKE to the longest
 // node's list (Tuples.cxx:346-377).  If counts != nullptr it receives every node's real count.
 //
@@ -90,45 +147,11 @@ inline bool takes(const Key &k, uint64_t me, uint64_t pos, uint64_t sz) {
 // reference's own special_distribution and with the oracle).
 inline std::vector<Tuple> group_and_sort_tuples(uint64_t Nv, uint64_t me, uint64_t n, bool pad = true,
                                                 std::vector<uint64_t> *counts = nullptr) {
-  const uint64_t nkeys = n * n * n;
-  // key of every residue triple (ra, rb, rc)
-  std::vector<gs::Key> keys(nkeys);
-  std::vector<uint32_t> kid(nkeys);
-  for (uint64_t ra = 0; ra < n; ra++)
-    for (uint64_t rb = 0; rb < n; rb++)
-      for (uint64_t rc = 0; rc < n; rc++) {
-        const gs::Key k = gs::key_of(ra, rb, rc, n);
-        keys[(ra * n + rb) * n + rc] = k;
-        kid[(ra * n + rb) * n + rc] = (uint32_t)k.id(n);
-      }
-  // number of c in [lo, Nv) with c % n == r
-  auto count_c = [&](uint64_t lo, uint64_t r) -> uint64_t {
-    const uint64_t first = lo + (r + n - lo % n) % n;
-    return first < Nv ? (Nv - 1 - first) / n + 1 : 0;
-  };
-  std::vector<uint64_t> size(nkeys, 0), seen(nkeys, 0);
-  for (uint64_t a = 0; a < Nv; a++)
-    for (uint64_t b = a; b < Nv; b++) {
-      const uint64_t lo = b + (a == b ? 1 : 0);  // a == b == c is not a tuple
-      const uint64_t base = ((a % n) * n + b % n) * n;
-      for (uint64_t r = 0; r < n; r++) size[kid[base + r]] += count_c(lo, r);
-    }
-  // every node's count follows from the container sizes alone
-  std::vector<uint64_t> cnt(n, 0);
-  for (uint64_t x = 0; x < n; x++) {
-    cnt[x] += size[x + x * n + x * n * n];  // one home node: the whole container
-    for (uint64_t y = x + 1; y < n; y++) {
-      const uint64_t s2 = size[x + y * n + y * n * n];  // two home nodes: halves
-      cnt[x] += s2 / 2;
-      cnt[y] += s2 - s2 / 2;
-      for (uint64_t z = y + 1; z < n; z++) {
-        const uint64_t s3 = size[x + y * n + z * n * n];  // three: thirds
-        cnt[x] += s3 / 3;
-        cnt[y] += s3 / 3;
-        cnt[z] += s3 - 2 * (s3 / 3);
-      }
-    }
-  }
+  const gs::Census C = gs::census(Nv, n);
+  const std::vector<gs::Key> &keys = C.keys;
+  const std::vector<uint32_t> &kid = C.kid;
+  const std::vector<uint64_t> &size = C.size, &cnt = C.cnt;
+  std::vector<uint64_t> seen(n * n * n, 0);
   if (counts) *counts = cnt;
   // my share, with the home elements moved to the back so that the non-home indices vary slowest
   // after sorting (:267-286); packed as t0 << 42 | t1 << 21 | t2 for the sort
