@@ -238,6 +238,7 @@ struct atrip_b200_ctx {
   double timing[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   int last_nt = 0, last_buf = 0;  // tuples and cube buffer of the last batch run (debug checksum)
   bool reduce_async = false;      // ATRIP_B200_REDUCE=async: experimental bulk-copy reduction (reduction_async.cuh)
+  bool reduce_reverse = false;    // ATRIP_B200_REDUCE=async-rev: ... walking the batch last tuple first
 };
 
 namespace {
@@ -421,6 +422,7 @@ ReduceParams reduce_params(atrip_b200_ctx *c, const TupleRec *d_recs, int ntuple
     if (score > best_score + 1e-9) { best_score = score; best = ns; }
   }
   P.nsplit = best;
+  P.reverse = c->reduce_reverse ? 1 : 0;
   if (const char *e = std::getenv("ATRIP_B200_NSPLIT")) {  // developer knob: force the orbit split
     const int v = std::atoi(e);
     if (v >= 1) P.nsplit = std::min(v, std::min(orbits, 64));
@@ -500,7 +502,10 @@ void create_impl(atrip_b200_ctx *c) {
                                (int)reduce_smem_bytes(c->No, false)));
   CUDA_OK(cudaFuncSetAttribute((const void *)reduce_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)reduce_smem_bytes(c->No, true)));
-  if (const char *e = std::getenv("ATRIP_B200_REDUCE")) c->reduce_async = std::string(e) == "async" && !c->cplx;
+  if (const char *e = std::getenv("ATRIP_B200_REDUCE")) {
+    c->reduce_reverse = std::string(e) == "async-rev";
+    c->reduce_async = (std::string(e) == "async" || c->reduce_reverse) && !c->cplx;
+  }
   if (c->reduce_async)
     CUDA_OK(cudaFuncSetAttribute((const void *)reduce_async_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)reduce_async_smem_bytes(c->No)));

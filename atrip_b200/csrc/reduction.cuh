@@ -46,6 +46,8 @@ struct ReduceParams {
   int ownedV;
   double *e_tuple;    // [ntuples * nsplit] partial energies
   int nsplit;         // CTAs per tuple: CTA (t, s) takes the orbits o with o % nsplit == s
+  int reverse;        // experimental kernels only: walk the batch's tuples last-to-first (the cubes the
+                      // contraction wrote last are the ones still resident in L2)
 };
 
 __host__ __device__ inline size_t reduce_smem_bytes(int No, bool ct) {

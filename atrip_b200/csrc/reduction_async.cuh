@@ -1,4 +1,4 @@
-// Kernel 2, experimental variant (opt-in: ATRIP_B200_REDUCE=async; real field, (T) pass only).
+// Kernel 2, experimental variant (opt-in: ATRIP_B200_REDUCE=async or async-rev; real field, (T) pass only).
 //
 // Same mathematics, orbit walk, tile layout and per-point operation order as reduce_kernel
 // (reduction.cuh) -- only the way the class-cube tiles reach shared memory differs.  ncu of
@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(REDUCE_THREADS, 2) reduce_async_kernel(const R
   double *sRed = sTc + P.No;                    // [32]
   uint64_t *bar = reinterpret_cast<uint64_t *>(sRed + 32);
 
-  const int tup = blockIdx.x;
+  const int tup = P.reverse ? P.ntuples - 1 - (int)blockIdx.x : (int)blockIdx.x;
   const TupleRec rec = P.recs[tup];
   const int tid = threadIdx.x;
   const int split = blockIdx.y;

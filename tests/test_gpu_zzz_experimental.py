@@ -42,11 +42,12 @@ def totals(No, Nv, reduce_mode):
 
 
 @pytest.mark.xfail(strict=False, reason="reduce_async_kernel (ATRIP_B200_REDUCE=async) has not run on a GPU yet")
+@pytest.mark.parametrize("mode", ["async", "async-rev"])
 @pytest.mark.parametrize("No,Nv", [(8, 16), (16, 24), (33, 40), (40, 56)])
-def test_async_reduction_matches_default(No, Nv):
+def test_async_reduction_matches_default(No, Nv, mode):
     want = totals(No, Nv, None)
     try:
-        got = totals(No, Nv, "async")
+        got = totals(No, Nv, mode)
     except subprocess.TimeoutExpired:
         pytest.fail("the experimental reduction did not finish within 120 s (killed)")
     assert np.all(np.abs(got - want) <= 1e-13 * np.abs(want)), (got, want)
