@@ -1,6 +1,6 @@
 """developer smoke: engine vs oracle on a few sizes (GPU box)"""
 import sys, time, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from oracle.oracle import Oracle, EPS_I, EPS_A, TAI, TABIJ, VABIJ, VIJKA, VABCI
 import atrip_b200
