@@ -1232,7 +1232,7 @@ int guarded(atrip_b200_ctx *c, F f) {
 extern "C" {
 
 const char *atrip_b200_last_error(void) { return g_error.c_str(); }
-const char *atrip_b200_version(void) { return "atrip_b200 0.1 (sm_100a)"; }
+const char *atrip_b200_version(void) { return "atrip_b200 0.2 (sm_100a)"; }
 int32_t atrip_b200_device_count(void) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess) {
