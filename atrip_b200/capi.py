@@ -26,12 +26,15 @@ SYMBOLS = [
     "atrip_b200_host_slice_slot", "atrip_b200_host_shard_sizes", "atrip_b200_host_plan_batch",
     "atrip_b200_host_cache_need", "atrip_b200_host_local_slot", "atrip_b200_host_store_source",
     "atrip_b200_host_energy_z", "atrip_b200_debug_cubes_checksum",
+    "atrip_b200_upload_slices", "atrip_b200_upload_slice", "atrip_b200_read_slices",
+    "atrip_b200_host_owned_slices", "atrip_b200_last_phases", "atrip_b200_host_check_schedule",
 ]
 
 NAIVE, GROUP_AND_SORT = 0, 1
 FIELD_REAL, FIELD_COMPLEX = 0, 1
 TRANSPORT_DEFAULT, TRANSPORT_NCCL, TRANSPORT_P2P = 0, 1, 2
 TA, VIJKA, VABCI, TABIJ, VABIJ = 100, 101, 200, 201, 202
+JIJKA, JABCI = 111, 210  # (cT) tensors in the slice kinds of the upload / read-back entry points
 VABCI_T = 203  # host-side name of the transposed-hole twin (x,x)' of a diagonal pair slice
 
 
@@ -109,6 +112,14 @@ def load_library():
                                              C.POINTER(C.c_int32), _ip, C.c_int64]
     L.atrip_b200_host_plan_batch.restype = C.c_int64
     L.atrip_b200_host_cache_need.argtypes = [C.c_int64, C.c_int32, C.c_int32, _up, C.c_int64, C.c_int64, _ip]
+    L.atrip_b200_host_check_schedule.argtypes = [C.c_int64, C.c_int32, C.c_int32, _up, C.c_int64, C.c_int64, C.c_int32,
+                                                 _ip, _dp]
+    L.atrip_b200_upload_slices.argtypes = [ctx, C.c_int32, C.c_int64, _ip, _dp]
+    L.atrip_b200_upload_slice.argtypes = [ctx, C.c_int32, C.c_int64, C.c_int64, _dp]
+    L.atrip_b200_read_slices.argtypes = [ctx, C.c_int32, C.c_int64, _ip, _dp]
+    L.atrip_b200_host_owned_slices.argtypes = [C.c_int32, C.c_int64, C.c_int32, C.c_int32, _ip, C.c_int64]
+    L.atrip_b200_host_owned_slices.restype = C.c_int64
+    L.atrip_b200_last_phases.argtypes = [ctx, _dp]
     L.atrip_b200_comm_unique_id.argtypes = [C.c_void_p]
     L.atrip_b200_comm_init.argtypes = [ctx, C.c_void_p]
     L.atrip_b200_allreduce.argtypes = [ctx, _dp, C.c_int32]
@@ -213,6 +224,30 @@ def cache_need(Nv, rank, nranks, abc, batch):
     if L.atrip_b200_host_cache_need(Nv, rank, nranks, abc.ctypes.data_as(_up), len(abc), batch, out) != 0:
         raise EngineError(L.atrip_b200_last_error().decode())
     return tuple(out)
+
+
+def check_schedule(Nv, rank, nranks, abc, batch, caps, calls=1):
+    """walk a tuple list through the persistent fetch cache as atrip_b200_run does and check it against an
+    independent model (host-only); returns the traffic statistics, raises EngineError on a violation"""
+    L = load_library()
+    abc = np.ascontiguousarray(abc, dtype=np.uint64).reshape(-1, 3)
+    cap = (C.c_int64 * 3)(*[int(x) for x in caps])
+    out = (C.c_double * 8)()
+    if L.atrip_b200_host_check_schedule(Nv, rank, nranks, abc.ctypes.data_as(_up), len(abc), batch, calls, cap, out) != 0:
+        raise EngineError(L.atrip_b200_last_error().decode())
+    return dict(fetched=[int(out[i]) for i in range(3)], hits=[int(out[3 + i]) for i in range(3)],
+                ranges=int(out[6]), batches=int(out[7]))
+
+
+def owned_slices(kind, Nv, rank, nranks):
+    """(x, y) list [n,2] int64 of the slices of `kind` a rank has to be given (host-only)"""
+    L = load_library()
+    n = L.atrip_b200_host_owned_slices(kind, Nv, rank, nranks, None, 0)
+    if n < 0:
+        raise EngineError(L.atrip_b200_last_error().decode())
+    out = np.zeros((n, 2), dtype=np.int64)
+    L.atrip_b200_host_owned_slices(kind, Nv, rank, nranks, out.ctypes.data_as(C.POINTER(C.c_int64)), n)
+    return out
 
 
 def comm_unique_id():
@@ -348,6 +383,34 @@ class Engine:
         out = np.empty(n, dtype=self.dtype)
         self._ck(self.L.atrip_b200_read_slice(self.ctx, kind, x, y, _ptr(out)))
         return out
+
+    def slice_elems(self, kind):
+        No, Nv = self.No, self.Nv
+        return {TA: Nv * No * No, VIJKA: No ** 3, JIJKA: No ** 3, VABCI: Nv * No, JABCI: Nv * No, TABIJ: No * No,
+                VABIJ: No * No}[kind]
+
+    def upload_slices(self, kind, xy, host):
+        """n slices of one kind in the reference's slice layout, back to back (numpy array or address)"""
+        xy = np.ascontiguousarray(xy, dtype=np.int64).reshape(-1, 2)
+        self._ck(self.L.atrip_b200_upload_slices(self.ctx, kind, len(xy), xy.ctypes.data_as(C.POINTER(C.c_int64)),
+                                                 _ptr(host)))
+
+    def upload_slice(self, kind, x, y, host):
+        self._ck(self.L.atrip_b200_upload_slice(self.ctx, kind, x, y, _ptr(host)))
+
+    def read_slices(self, kind, xy, out=None):
+        xy = np.ascontiguousarray(xy, dtype=np.int64).reshape(-1, 2)
+        if out is None:
+            out = np.empty(len(xy) * self.slice_elems(kind), dtype=self.dtype)
+        self._ck(self.L.atrip_b200_read_slices(self.ctx, kind, len(xy), xy.ctypes.data_as(C.POINTER(C.c_int64)),
+                                               _ptr(out)))
+        return out
+
+    def last_phases(self):
+        out = (C.c_double * 6)()
+        self.L.atrip_b200_last_phases(self.ctx, out)
+        return dict(gap_ms=out[0], plan_ms=out[1], cache_hits=int(out[2]), fetched=int(out[3]), batches=int(out[4]),
+                    startup_gap_ms=out[5])
 
     # ---- multi-GPU
     def comm_init(self, unique_id):

@@ -72,6 +72,14 @@ __device__ __forceinline__ void fence_barrier_init() {
 __device__ __forceinline__ void fence_proxy_async() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
+// consumer-side release of a TMA ring stage: orders this thread's generic-proxy shared-memory
+// reads before async-proxy writes that follow in the mbarrier-mediated order (contraction.cuh).
+// -DATRIP_B200_NO_RELEASE_FENCE builds the unfenced variant for A/B timing only.
+__device__ __forceinline__ void release_fence() {
+#ifndef ATRIP_B200_NO_RELEASE_FENCE
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *tm) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
 }

@@ -202,14 +202,18 @@ contract_kernel(const __grid_constant__ ContractMaps M, const ContractParams P) 
         if (P.last_steps > 2) kstep(cs[2]);
         if (P.last_steps > 3) kstep(cs[3]);
       }
-      // Hand the stage back only after every fragment load of it has delivered its data.  The
-      // loads are consumed by DMMAs, which wait for their operands at issue, so "after all DMMAs
-      // of the stage in program order" is sufficient -- but ptxas may move the arrive (it has no
-      // register dependency) anywhere inside a basic block: a former straight-line variant of
-      // this loop body (no tail branch) had the arrive scheduled between the last LDS and its
-      // DMMAs and produced run-to-run different cubes (profiles/r01_ring_release_race.txt).  The
-      // two-way branch above ends the basic block that holds the loads; tools/check_sass_order.py
-      // (run by tests/test_host.py) asserts  last DMMA < WARPSYNC < arrive  in every instantiation.
+      // Hand the stage back only after every fragment load of it has delivered its data: the
+      // producer's refill is a TMA write (async proxy) over rows this warp read through the
+      // generic proxy.  The ordering construct is the proxy fence every lane executes before the
+      // warp-level rendezvous: generic-proxy reads (the LDS above) -> fence.proxy.async ->
+      // __syncwarp -> mbarrier.arrive (release) -> producer's wait (acquire) -> TMA write.  Without
+      // it nothing in the source ties the arrive to the loads (it has no register dependency) and
+      // ptxas once scheduled it between the last LDS and the DMMAs consuming them in a
+      // straight-line variant of this loop body: run-to-run different cubes
+      // (profiles/r01_ring_release_race.txt).  tools/check_sass_order.py (run by
+      // tests/test_host.py) stays as a second guard: it asserts  last LDS < FENCE < WARPSYNC <
+      // arrive  and  last DMMA < arrive  in the SASS of every instantiation.
+      release_fence();
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty_bar[stage]);
       if (++stage == P.nstages) { stage = 0; phase ^= 1; }

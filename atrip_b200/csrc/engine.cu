@@ -4,6 +4,7 @@
 // There is deliberately no CPU path in this file: every compute entry point needs the CUDA
 // device and fails loudly without it.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -173,6 +174,14 @@ struct Scratch {
 }  // namespace
 
 constexpr int REC_RING = 4;  // batches the host may run ahead of the device
+constexpr int NXS = 4;       // copy streams of the P2P transport (the pulls of a batch are dealt round-robin)
+constexpr int TRING = 8;     // per-batch timing events are harvested TRING batches later
+
+// timing events of one batch: [w0, c0] = gap in front of the contraction launch (slice fetch not yet
+// landed, cube buffer not yet reduced), [c0, c1] contraction, [r0, r1] reduction + batch sum
+struct BatchTimers {
+  cudaEvent_t w0 = nullptr, c0 = nullptr, c1 = nullptr, r0 = nullptr, r1 = nullptr;
+};
 
 struct atrip_b200_ctx {
   atrip_b200_config cfg{};
@@ -184,7 +193,10 @@ struct atrip_b200_ctx {
   // contraction (high priority); reduction of the previous batch (low priority, runs beside the
   // next contraction on the same SMs); slice exchange (side stream)
   cudaStream_t stream = nullptr, rstream = nullptr, xstream = nullptr;
+  cudaStream_t xs[NXS]{};  // xs[0] == xstream
+  cudaEvent_t xfork = nullptr, xjoin[NXS]{};
   cudaEvent_t ev[6]{};
+  BatchTimers bt[TRING];
 
   // stores: owned slices in the layouts of stores.cuh, slot numbering of schedule.hpp
   ShardMap map;                // storage sharding (replica: n = 1)
@@ -196,9 +208,12 @@ struct atrip_b200_ctx {
   int *xlist = nullptr, *ylist = nullptr, *zlist = nullptr, *tflag = nullptr, *vy = nullptr, *vz = nullptr;
   bool have_J = false;
 
-  // fetch caches (sharded stores only): two regions of cap[kind] slots, used by alternate batches
+  // fetch caches (sharded stores only): cap[kind] slots per store, managed by SliceCache
+  // (schedule.hpp): slices stay until their slot is re-assigned, two batches after their last use
   int64_t cap[3] = {0, 0, 0};
   double *cA = nullptr, *cB = nullptr, *cV = nullptr, *cAJ = nullptr, *cBJ = nullptr;
+  SliceCache cache;
+  int64_t serial = 0;  // number of the next batch (monotonic over runs)
 
   // tuples
   std::vector<Tuple> tuples;
@@ -235,7 +250,7 @@ struct atrip_b200_ctx {
   size_t stage_elems = 0;
   cudaEvent_t stage_ev[2]{};
 
-  double timing[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  double timing[16] = {0};
   int last_nt = 0, last_buf = 0;  // tuples and cube buffer of the last batch run (debug checksum)
   bool reduce_async = false;      // ATRIP_B200_REDUCE=async: experimental bulk-copy reduction (reduction_async.cuh)
   bool reduce_reverse = false;    // ATRIP_B200_REDUCE=async-rev: ... walking the batch last tuple first
@@ -280,11 +295,11 @@ void build_all_maps(atrip_b200_ctx *c) {
   for (int var = 0; var <= c->cplx; var++) {
     ContractMaps &M = var ? c->maps1 : c->maps, &MJ = var ? c->mapsJ1 : c->mapsJ;
     build_maps(c, c->AX, c->owned[KA], c->BY, c->owned[KB], &M.A, &M.AT, &M.B, var);
-    if (c->cA) build_maps(c, c->cA, 2 * c->cap[KA], c->cB, 2 * c->cap[KB], &M.Ac, &M.ATc, &M.Bc, var);
+    if (c->cA) build_maps(c, c->cA, c->cap[KA], c->cB, c->cap[KB], &M.Ac, &M.ATc, &M.Bc, var);
     else { M.Ac = M.A; M.ATc = M.AT; M.Bc = M.B; }
     if (c->cfg.with_J) {
       build_maps(c, c->AXJ, c->owned[KA], c->BYJ, c->owned[KB], &MJ.A, &MJ.AT, &MJ.B, var);
-      if (c->cAJ) build_maps(c, c->cAJ, 2 * c->cap[KA], c->cBJ, 2 * c->cap[KB], &MJ.Ac, &MJ.ATc, &MJ.Bc, var);
+      if (c->cAJ) build_maps(c, c->cAJ, c->cap[KA], c->cBJ, c->cap[KB], &MJ.Ac, &MJ.ATc, &MJ.Bc, var);
       else { MJ.Ac = MJ.A; MJ.ATc = MJ.AT; MJ.Bc = MJ.B; }
     }
   }
@@ -292,24 +307,30 @@ void build_all_maps(atrip_b200_ctx *c) {
 
 bool sharded(const atrip_b200_ctx *c) { return c->map.n > 1; }
 
-// fetch caches sized for the current tuple list (schedule.hpp: cache_need); grown on demand
+// fetch caches sized for the current tuple list (schedule.hpp: cache_need = distinct remote slices
+// of any window of one batch): three windows -- the batch computing, the batch being fetched and the
+// batch prefetched for the next run call; grown on demand
 void ensure_caches(atrip_b200_ctx *c, const int64_t need[3]) {
   if (!sharded(c)) return;
   // a debug tuple (12 slices, all remote in the worst case) must always fit
-  const int64_t want[3] = {std::max<int64_t>(need[KA], 3), std::max<int64_t>(need[KB], 6), std::max<int64_t>(need[KV], 3)};
+  const int64_t want[3] = {std::max<int64_t>(3 * need[KA], 3), std::max<int64_t>(3 * need[KB], 6),
+                           std::max<int64_t>(3 * need[KV], 3)};
   if (c->cA && want[KA] <= c->cap[KA] && want[KB] <= c->cap[KB] && want[KV] <= c->cap[KV]) return;
   CUDA_OK(cudaStreamSynchronize(c->stream));
   CUDA_OK(cudaStreamSynchronize(c->xstream));
   for (double **p : {&c->cA, &c->cB, &c->cV, &c->cAJ, &c->cBJ})
     if (*p) { cudaFree(*p); *p = nullptr; }
   for (int k = 0; k < 3; k++) c->cap[k] = std::max(c->cap[k], want[k]);
-  c->cA = dalloc<double>(2 * c->cap[KA] * slice_elems(c, KA));
-  c->cB = dalloc<double>(2 * c->cap[KB] * slice_elems(c, KB));
-  c->cV = dalloc<double>(2 * c->cap[KV] * slice_elems(c, KV));
+  REQUIRE(c->owned[KB] + c->cap[KB] < (1LL << 31) && c->owned[KV] + c->cap[KV] < (1LL << 31),
+          "too many slots for 32-bit slot numbers");
+  c->cA = dalloc<double>(c->cap[KA] * slice_elems(c, KA));
+  c->cB = dalloc<double>(c->cap[KB] * slice_elems(c, KB));
+  c->cV = dalloc<double>(c->cap[KV] * slice_elems(c, KV));
   if (c->cfg.with_J) {
-    c->cAJ = dalloc<double>(2 * c->cap[KA] * slice_elems(c, KA));
-    c->cBJ = dalloc<double>(2 * c->cap[KB] * slice_elems(c, KB));
+    c->cAJ = dalloc<double>(c->cap[KA] * slice_elems(c, KA));
+    c->cBJ = dalloc<double>(c->cap[KB] * slice_elems(c, KB));
   }
+  c->cache.reset(c->cap);
   build_all_maps(c);
 }
 
@@ -487,6 +508,12 @@ void create_impl(atrip_b200_ctx *c) {
   CUDA_OK(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_greatest));
   CUDA_OK(cudaStreamCreateWithPriority(&c->rstream, cudaStreamNonBlocking, prio_least));
   CUDA_OK(cudaStreamCreateWithFlags(&c->xstream, cudaStreamNonBlocking));
+  c->xs[0] = c->xstream;
+  for (int i = 1; i < NXS; i++) CUDA_OK(cudaStreamCreateWithFlags(&c->xs[i], cudaStreamNonBlocking));
+  CUDA_OK(cudaEventCreateWithFlags(&c->xfork, cudaEventDisableTiming));
+  for (int i = 1; i < NXS; i++) CUDA_OK(cudaEventCreateWithFlags(&c->xjoin[i], cudaEventDisableTiming));
+  for (auto &b : c->bt)
+    for (cudaEvent_t *e : {&b.w0, &b.c0, &b.c1, &b.r0, &b.r1}) CUDA_OK(cudaEventCreate(e));
   for (auto &ev : c->ev) CUDA_OK(cudaEventCreate(&ev));
   for (auto &ev : c->rec_ev) CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   for (auto &ev : c->xdone) CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -656,6 +683,12 @@ void destroy_impl(atrip_b200_ctx *c) {
       if (evs[i]) cudaEventDestroy(evs[i]);
   };
   kill(c->ev, 6);
+  for (auto &b : c->bt)
+    for (cudaEvent_t *e : {&b.w0, &b.c0, &b.c1, &b.r0, &b.r1}) kill(e, 1);
+  kill(&c->xfork, 1);
+  kill(c->xjoin, NXS);
+  for (int i = 1; i < NXS; i++)
+    if (c->xs[i]) cudaStreamDestroy(c->xs[i]);
   kill(c->stage_ev, 2);
   kill(c->rec_ev, REC_RING);
   kill(c->xdone, 4);
@@ -669,9 +702,21 @@ void destroy_impl(atrip_b200_ctx *c) {
   delete c;
 }
 
+void rank_barrier(atrip_b200_ctx *c);
+
+// The stores are about to change.  With the P2P transport the peers read this rank's stores
+// directly: once the ranks have run tuples, a peer may still be pulling slices of its previous run,
+// so (re)loading sharded stores after a run is collective -- wait until every rank got here.  The
+// first run after the update synchronises the ranks again (run_list) before anybody reads.
+void begin_store_update(atrip_b200_ctx *c) {
+  if (sharded(c) && c->comm && c->transport == 2 && !c->stores_dirty) rank_barrier(c);
+  c->stores_dirty = true;
+}
+
 int grid_for(size_t n, int nsm) { return (int)std::min<size_t>((n + 255) / 256, (size_t)nsm * 16); }
 
 void fill_z_impl(atrip_b200_ctx *c, uint64_t seed, double scale) {
+  begin_store_update(c);
   const StoreDims d = dims_of(c);
   const size_t No = c->No;
   const size_t nX = c->owned[KA], nB = c->owned[KB], nV = c->owned[KV];
@@ -697,6 +742,7 @@ void fill_z_impl(atrip_b200_ctx *c, uint64_t seed, double scale) {
 
 void fill_impl(atrip_b200_ctx *c, uint64_t seed, double scale) {
   if (c->cplx) return fill_z_impl(c, seed, scale);
+  begin_store_update(c);
   const StoreDims d = dims_of(c);
   const size_t No = c->No;
   const size_t nX = c->owned[KA], nB = c->owned[KB], nV = c->owned[KV];
@@ -810,6 +856,107 @@ void load_ppph_impl(atrip_b200_ctx *c, const double *V, double *BY) {
   CUDA_OK(cudaGetLastError());
 }
 
+
+// ------------------------------------------------------------------ per-slice ingest / read-back
+size_t ref_slice_elems(const atrip_b200_ctx *c, int kind) {  // elements (F) of a slice in the reference layout
+  const size_t No = c->No, Nv = c->Nv;
+  switch (kind) {
+    case 100: return Nv * No * No;
+    case 101: case 111: return No * No * No;
+    case 200: case 210: return Nv * No;
+    case 201: case 202: return No * No;
+  }
+  throw Fail{"unknown slice kind"};
+}
+
+void check_xy(const atrip_b200_ctx *c, int kind, int64_t n, const int64_t *xy) {
+  const int64_t Nv = c->Nv;
+  for (int64_t i = 0; i < n; i++) {
+    const int64_t x = xy[2 * i], y = xy[2 * i + 1];
+    REQUIRE(x >= 0 && x < Nv, "slice index x out of range");
+    if (kind >= 200) REQUIRE(y >= 0 && y < Nv, "slice index y out of range");
+    if (kind == 201 || kind == 202) REQUIRE(x <= y, "TABIJ / VABIJ slices are addressed with x <= y");
+  }
+}
+
+// Replaces SliceUnion<F>::init (SliceUnion.cxx:305-332) for one kind: n slices in the reference's
+// slice layout, back to back in host memory, go through the staging pair in chunks and are
+// scattered into the stores; slices this rank does not hold are skipped.  Pinned host memory is read
+// by DMA straight from the caller's buffer (asynchronously: atrip_b200_upload_flush).
+void upload_slices_impl(atrip_b200_ctx *c, int kind, int64_t n, const int64_t *xy, const double *host) {
+  const size_t per = ref_slice_elems(c, kind) * esz(c);  // doubles per slice
+  REQUIRE(n >= 0, "negative slice count");
+  if (n == 0) return;
+  check_xy(c, kind, n, xy);
+  const bool J = kind == 111 || kind == 210;
+  REQUIRE(!J || c->cfg.with_J, "context was created without with_J");
+  begin_store_update(c);
+  const int base_kind = kind == 111 ? 101 : (kind == 210 ? 200 : kind);
+  const size_t chunk_slices = std::max<size_t>(1, (size_t)(48u << 20) / (per * 8));
+  ensure_stage(c, chunk_slices * per);
+  Scratch<long long> dxy((size_t)2 * std::min<size_t>(chunk_slices, (size_t)n) * 2);
+  const bool pinned = is_pinned(host);
+  const SliceTables tb{c->xtab, c->btab, c->vtab};
+  const StoreDims d = dims_of(c);
+  size_t k = 0;
+  for (int64_t s0 = 0; s0 < n; s0 += (int64_t)chunk_slices, k++) {
+    const size_t ns = (size_t)std::min<int64_t>((int64_t)chunk_slices, n - s0);
+    const int st = (int)(k & 1);
+    CUDA_OK(cudaEventSynchronize(c->stage_ev[st]));
+    const double *src = host + (size_t)s0 * per;
+    if (!pinned) {
+      std::memcpy(c->h_stage[st], src, ns * per * 8);
+      src = c->h_stage[st];
+    }
+    long long *dx = dxy.p + (size_t)st * 2 * std::min<size_t>(chunk_slices, (size_t)n);
+    CUDA_OK(cudaMemcpyAsync(dx, xy + 2 * s0, ns * 2 * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(cudaMemcpyAsync(c->d_stage[st], src, ns * per * 8, cudaMemcpyHostToDevice, c->stream));
+    const int grid = grid_for(ns * ref_slice_elems(c, kind), c->nsm);
+    auto launch = [&](double *AX, double *BY) {
+      if (c->cplx) upload_slices_kernel<true><<<grid, 256, 0, c->stream>>>(base_kind, c->d_stage[st], dx, (int)ns, d, tb, AX, BY, c->VIJ);
+      else upload_slices_kernel<false><<<grid, 256, 0, c->stream>>>(base_kind, c->d_stage[st], dx, (int)ns, d, tb, AX, BY, c->VIJ);
+    };
+    if (J) launch(c->AXJ, c->BYJ);
+    else {
+      launch(c->AX, c->BY);
+      // the J stores share the amplitudes (Tabij) with the V stores
+      if (c->cfg.with_J && (kind == 100 || kind == 201)) launch(c->AXJ, c->BYJ);
+    }
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaEventRecord(c->stage_ev[st], c->stream));
+  }
+  if (J) c->have_J = true;
+  // pageable sources were consumed by the memcpy above; the device work may still be in flight
+  // (the slot tables dxy are freed below: wait for the kernels that read them)
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+}
+
+void read_slices_impl(atrip_b200_ctx *c, int kind, int64_t n, const int64_t *xy, double *out) {
+  const size_t per = ref_slice_elems(c, kind) * esz(c);
+  REQUIRE(n >= 0, "negative slice count");
+  if (n == 0) return;
+  check_xy(c, kind, n, xy);
+  const bool J = kind == 111 || kind == 210;
+  REQUIRE(!J || c->cfg.with_J, "context was created without with_J");
+  const int base_kind = kind == 111 ? 101 : (kind == 210 ? 200 : kind);
+  const size_t chunk_slices = std::max<size_t>(1, (size_t)(48u << 20) / (per * 8));
+  Scratch<double> dbuf(std::min<size_t>(chunk_slices, (size_t)n) * per);
+  Scratch<long long> dxy((size_t)2 * std::min<size_t>(chunk_slices, (size_t)n));
+  const SliceTables tb{c->xtab, c->btab, c->vtab};
+  const StoreDims d = dims_of(c);
+  for (int64_t s0 = 0; s0 < n; s0 += (int64_t)chunk_slices) {
+    const size_t ns = (size_t)std::min<int64_t>((int64_t)chunk_slices, n - s0);
+    CUDA_OK(cudaMemcpyAsync(dxy.p, xy + 2 * s0, ns * 2 * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
+    const int grid = grid_for(ns * ref_slice_elems(c, kind), c->nsm);
+    const double *AX = J ? c->AXJ : c->AX, *BY = J ? c->BYJ : c->BY;
+    if (c->cplx) read_slices_kernel<true><<<grid, 256, 0, c->stream>>>(base_kind, dbuf.p, dxy.p, (int)ns, d, tb, AX, BY, c->VIJ);
+    else read_slices_kernel<false><<<grid, 256, 0, c->stream>>>(base_kind, dbuf.p, dxy.p, (int)ns, d, tb, AX, BY, c->VIJ);
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaMemcpyAsync(out + (size_t)s0 * per, dbuf.p, ns * per * 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+  }
+}
+
 // ------------------------------------------------------------------ slice exchange (NCCL)
 #define NCCL_OK(expr)                                                                              \
   do {                                                                                             \
@@ -834,7 +981,7 @@ double *cache_of(const atrip_b200_ctx *c, int kind, bool J) {
 // time): inside one NCCL group
 //   data     for batch `k`:  send the ranges every peer asked of me (peer_req, host copy of the
 //            request lists received one step earlier), receive the ranges of my own plan into
-//            cache region k % 2;
+//            the cache slots the plan assigned;
 //   requests for batch k+1:  send my request lists (next != nullptr), receive the peers'.
 // k = -1 is the bootstrap step that only exchanges the request lists of batch 0.
 void exchange_step(atrip_b200_ctx *c, int64_t k, const BatchPlan *mine, const BatchPlan *next) {
@@ -867,7 +1014,7 @@ void exchange_step(atrip_b200_ctx *c, int64_t k, const BatchPlan *mine, const Ba
       }
       for (const FetchRange &fr : mine->fetch[(size_t)p]) {
         const size_t el = slice_elems(c, fr.kind);
-        const size_t dst = (size_t)(par * c->cap[fr.kind] + fr.dst_slot) * el;
+        const size_t dst = (size_t)fr.dst_slot * el;
         NCCL_OK(N.Recv(cache_of(c, fr.kind, false) + dst, (size_t)fr.count * el, ncclFloat64, p, c->comm, c->xstream));
         if (J && fr.kind != KV)
           NCCL_OK(N.Recv(cache_of(c, fr.kind, true) + dst, (size_t)fr.count * el, ncclFloat64, p, c->comm, c->xstream));
@@ -895,67 +1042,108 @@ void rank_barrier(atrip_b200_ctx *c) {
   CUDA_OK(cudaStreamSynchronize(c->stream));
 }
 
-// P2P transport: pull the remote slices of one batch straight out of the owners' stores into
-// cache region `par` with the copy engines (NVLink / NVSwitch); nothing runs on an SM and the
-// owner is not involved.  Replaces SliceUnion::receive + send (SliceUnion.cxx:365-505).
-void pull_step(atrip_b200_ctx *c, const BatchPlan *mine, int par) {
+// P2P transport: pull the remote slices of one batch straight out of the owners' stores into the
+// cache slots of the plan with the copy engines (NVLink / NVSwitch); nothing runs on an SM and the
+// owner is not involved.  Replaces SliceUnion::receive + send (SliceUnion.cxx:365-505).  The copies
+// are dealt round-robin to NXS streams (a single stream serialises them: ~154 copies of 2.4 MB per
+// c2 batch took the whole batch time at 8 ranks); c->xstream is ordered behind all of them again.
+void pull_step(atrip_b200_ctx *c, const BatchPlan *mine) {
   const bool J = c->have_J;
+  size_t ncopies = 0;
+  for (const auto &v : mine->fetch) ncopies += v.size();
+  if (!ncopies) return;
+  const int ns = (int)std::min<size_t>(NXS, ncopies);
+  if (ns > 1) {
+    CUDA_OK(cudaEventRecord(c->xfork, c->xstream));
+    for (int i = 1; i < ns; i++) CUDA_OK(cudaStreamWaitEvent(c->xs[i], c->xfork, 0));
+  }
+  size_t i = 0;
   for (int p = 0; p < c->cfg.nranks; p++) {
     if (p == c->cfg.rank) continue;
     for (const FetchRange &fr : mine->fetch[(size_t)p]) {
       const size_t el = slice_elems(c, fr.kind);
-      const size_t dst = (size_t)(par * c->cap[fr.kind] + fr.dst_slot) * el, src = (size_t)fr.src_slot * el;
+      const size_t dst = (size_t)fr.dst_slot * el, src = (size_t)fr.src_slot * el;
       const size_t bytes = (size_t)fr.count * el * sizeof(double);
+      cudaStream_t st = c->xs[i++ % ns];
       CUDA_OK(cudaMemcpyAsync(cache_of(c, fr.kind, false) + dst, c->peer[fr.kind][(size_t)p] + src, bytes,
-                              cudaMemcpyDeviceToDevice, c->xstream));
+                              cudaMemcpyDeviceToDevice, st));
       if (J && fr.kind != KV)
         CUDA_OK(cudaMemcpyAsync(cache_of(c, fr.kind, true) + dst, c->peer[3 + fr.kind][(size_t)p] + src, bytes,
-                                cudaMemcpyDeviceToDevice, c->xstream));
+                                cudaMemcpyDeviceToDevice, st));
       c->exch_bytes += (double)bytes * ((J && fr.kind != KV) ? 2 : 1);
       c->exch_msgs += 1;
     }
   }
+  for (int q = 1; q < ns; q++) {
+    CUDA_OK(cudaEventRecord(c->xjoin[q], c->xs[q]));
+    CUDA_OK(cudaStreamWaitEvent(c->xstream, c->xjoin[q], 0));
+  }
 }
 
 // Runs the tuples list[0..count) in device batches.  Replaces the main loop, Atrip.cxx:686-1057.
-// Sharded stores: COLLECTIVE -- every rank calls with the same count; slices of batch k+1 travel
-// on the side stream while batch k computes (two cache regions).
-void run_list(atrip_b200_ctx *c, const Tuple *list, int64_t count, double *energy, double *ct_energy) {
+// Sharded stores: COLLECTIVE with the NCCL transport -- every rank calls with the same count;
+// slices of batch k+1 travel on the side stream(s) while batch k computes.  `next` (may be null):
+// the tuples the caller is likely to run next (the list continues there); with the P2P transport
+// their remote slices are prefetched behind the last batch, so that the next call does not start
+// with an exposed fetch.
+void run_list(atrip_b200_ctx *c, const Tuple *list, int64_t count, double *energy, double *ct_energy,
+              const Tuple *next = nullptr, int64_t next_count = 0) {
   const bool ct = c->have_J;
   const bool sh = sharded(c);
   REQUIRE(!sh || c->comm, "sharded stores need atrip_b200_comm_init before running tuples");
   REQUIRE(!sh || c->transport != 2 || !c->peer[0].empty(), "peer stores are not mapped");
   const int64_t nb = (count + c->batch - 1) / c->batch;
   auto nt_of = [&](int64_t k) { return (size_t)std::min<int64_t>(c->batch, count - k * c->batch); };
-  auto base_of = [&](int64_t k, int64_t base[3]) {
-    for (int q = 0; q < 3; q++) base[q] = c->owned[q] + (sh ? (k & 1) * c->cap[q] : 0);
-  };
-  BatchPlan plans[3];
-  auto make_plan = [&](int64_t k) {
-    int64_t base[3];
-    base_of(k, base);
-    BatchPlan &pl = plans[k % 3];
-    plan_batch(c->map, list + k * c->batch, nt_of(k), base, pl);
-    for (int q = 0; q < 3; q++)
-      REQUIRE(pl.used[q] <= c->cap[q] || !sh, "fetch cache too small for this batch (tuple list changed without set_tuples?)");
-  };
-  c->exch_bytes = c->exch_msgs = 0;
-  CUDA_OK(cudaMemsetAsync(c->d_total, 0, 2 * sizeof(double), c->stream));
-  double ms_contract = 0, ms_reduce = 0;
-  int n_contract = 0, n_reduce = 0, sampled = 0;
-  CUDA_OK(cudaEventRecord(c->ev[0], c->stream));
   const bool p2p = sh && c->transport == 2;
   if (sh && c->stores_dirty) {
-    rank_barrier(c);
+    rank_barrier(c);  // every rank has finished (re)filling its stores before anybody reads a peer's
     c->stores_dirty = false;
+    c->cache.invalidate();
   }
+  // everything of earlier runs has completed (each run ends with a full synchronisation): every
+  // cache slot may be re-assigned, and what the slots hold stays addressable
+  c->serial += 2;
+  const int64_t serial0 = c->serial;
+  BatchPlan plans[3];
+  double plan_ms = 0, hits = 0, misses = 0;
+  auto plan_tuples = [&](const Tuple *t, size_t n, int64_t serial, BatchPlan &pl, bool speculative) {
+    const auto h0 = std::chrono::steady_clock::now();
+    plan_batch(c->map, t, n, c->owned, c->cache, serial, pl);
+    plan_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count();
+    if (pl.overflow) {
+      c->cache.invalidate();  // the plan is half applied: drop every key (nothing in flight addresses them by key)
+      REQUIRE(speculative, "fetch cache too small for this batch (tuple list changed without set_tuples?)");
+      return false;
+    }
+    for (int q = 0; q < 3; q++) {
+      hits += (double)pl.hits[q];
+      misses += (double)pl.used[q];
+    }
+    return true;
+  };
+  auto make_plan = [&](int64_t k) { plan_tuples(list + k * c->batch, nt_of(k), serial0 + k, plans[k % 3], false); };
+  c->serial = serial0 + nb;
+  c->exch_bytes = c->exch_msgs = 0;
+  CUDA_OK(cudaMemsetAsync(c->d_total, 0, 2 * sizeof(double), c->stream));
+  double ms_gap = 0, ms_contract = 0, ms_reduce = 0;
+  int n_contract = 0, n_reduce = 0;
+  int64_t harvested = 0;
+  auto harvest = [&](int64_t k) {  // events of batch k have completed
+    const BatchTimers &b = c->bt[k % TRING];
+    float g = 0, a = 0, r = 0;
+    CUDA_OK(cudaEventElapsedTime(&g, b.w0, b.c0));
+    CUDA_OK(cudaEventElapsedTime(&a, b.c0, b.c1));
+    CUDA_OK(cudaEventElapsedTime(&r, b.r0, b.r1));
+    if (k > 0) ms_gap += g;  // batch 0: the gap is the start-up of the call, reported separately
+    else c->timing[13] = g;
+    ms_contract += a;
+    ms_reduce += r;
+  };
+  CUDA_OK(cudaEventRecord(c->ev[0], c->stream));
   if (nb > 0) make_plan(0);
   if (sh && nb > 0) {
-    // last run's compute may still read the caches / request buffers: order the side stream after it
-    CUDA_OK(cudaEventRecord(c->cdone[3], c->stream));
-    CUDA_OK(cudaStreamWaitEvent(c->xstream, c->cdone[3], 0));
     if (p2p) {
-      pull_step(c, &plans[0], 0);
+      pull_step(c, &plans[0]);
     } else {
       exchange_step(c, -1, nullptr, &plans[0]);
       CUDA_OK(cudaStreamSynchronize(c->xstream));
@@ -971,8 +1159,11 @@ void run_list(atrip_b200_ctx *c, const Tuple *list, int64_t count, double *energ
     const int slot = (int)(c->rec_uses % REC_RING);
     if (c->rec_uses >= REC_RING) CUDA_OK(cudaEventSynchronize(c->rec_ev[slot]));
     c->rec_uses++;
+    while (harvested + TRING <= k) harvest(harvested++);  // batch k - TRING is long done (REC_RING < TRING)
+    const BatchTimers &bt = c->bt[k % TRING];
     TupleRec *hr = c->h_recs + (size_t)slot * c->batch, *dr = c->d_recs + (size_t)slot * c->batch;
     std::memcpy(hr, pl.recs.data(), sizeof(TupleRec) * nt);
+    CUDA_OK(cudaEventRecord(bt.w0, c->stream));
     if (sh) CUDA_OK(cudaStreamWaitEvent(c->stream, c->xdone[k & 3], 0));
     CUDA_OK(cudaMemcpyAsync(dr, hr, sizeof(TupleRec) * nt, cudaMemcpyHostToDevice, c->stream));
     // ---- contraction of batch k on the high-priority stream into cube buffer k % 2 ...
@@ -983,14 +1174,12 @@ void run_list(atrip_b200_ctx *c, const Tuple *list, int64_t count, double *energ
     c->last_nt = nt;
     c->last_buf = buf;
     if (k >= 2) CUDA_OK(cudaStreamWaitEvent(c->stream, c->rdone[(k - 2) & 3], 0));  // buffer reduced
-    // per-kernel events around the first batches only: contraction [2,3], reduction [4,5]
-    const bool sample = sampled < 4;
-    if (sample) CUDA_OK(cudaEventRecord(c->ev[2], c->stream));
+    CUDA_OK(cudaEventRecord(bt.c0, c->stream));
     for (int var = 0; var <= c->cplx; var++) {  // complex field: Re cubes, then Im cubes
       launch_contract(c, dr, nt, false, buf, var);
       n_contract++;
     }
-    if (sample) CUDA_OK(cudaEventRecord(c->ev[3], c->stream));
+    CUDA_OK(cudaEventRecord(bt.c1, c->stream));
     CUDA_OK(cudaEventRecord(c->evV[k & 3], c->stream));
     if (ct) {
       for (int var = 0; var <= c->cplx; var++) {
@@ -1002,10 +1191,10 @@ void run_list(atrip_b200_ctx *c, const Tuple *list, int64_t count, double *energ
     CUDA_OK(cudaEventRecord(c->cdone[k & 3], c->stream));
     // ---- ... and its reduction on the low-priority stream
     CUDA_OK(cudaStreamWaitEvent(c->rstream, c->evV[k & 3], 0));
-    if (sample) CUDA_OK(cudaEventRecord(c->ev[4], c->rstream));
+    CUDA_OK(cudaEventRecord(bt.r0, c->rstream));
     launch_reduce(c, dr, nt, false, buf, c->d_total);
     n_reduce += 2;
-    if (sample) CUDA_OK(cudaEventRecord(c->ev[5], c->rstream));
+    CUDA_OK(cudaEventRecord(bt.r1, c->rstream));
     if (ct) {
       CUDA_OK(cudaStreamWaitEvent(c->rstream, c->evJ[k & 3], 0));
       launch_reduce(c, dr, nt, true, buf, c->d_total + 1);
@@ -1013,30 +1202,31 @@ void run_list(atrip_b200_ctx *c, const Tuple *list, int64_t count, double *energ
     }
     CUDA_OK(cudaEventRecord(c->rdone[k & 3], c->rstream));
     CUDA_OK(cudaEventRecord(c->rec_ev[slot], c->rstream));
-    // ---- next batch: host plan (and, sharded, its exchange on the side stream)
+    // ---- next batch: host plan (and, sharded, its exchange on the side stream).  The copies of
+    //      batch k+1 may overwrite slots last used by batch k-1: they wait for its reduction.
     if (k + 1 < nb) {
       if (!sh) make_plan(k + 1);
       else if (p2p) {  // fully asynchronous: the host never waits for a transfer
         make_plan(k + 1);
-        if (k >= 1) CUDA_OK(cudaStreamWaitEvent(c->xstream, c->rdone[(k - 1) & 3], 0));  // region (k+1)%2 is free
-        pull_step(c, &plans[(k + 1) % 3], (int)((k + 1) & 1));
+        if (k >= 1) CUDA_OK(cudaStreamWaitEvent(c->xstream, c->rdone[(k - 1) & 3], 0));
+        pull_step(c, &plans[(k + 1) % 3]);
         CUDA_OK(cudaEventRecord(c->xdone[(k + 1) & 3], c->xstream));
       } else {
         CUDA_OK(cudaEventSynchronize(c->xdone[k & 3]));  // peers' requests for batch k+1 are on the host
         if (k + 2 < nb) make_plan(k + 2);
-        if (k >= 1) CUDA_OK(cudaStreamWaitEvent(c->xstream, c->rdone[(k - 1) & 3], 0));  // region (k+1)%2 is free
+        if (k >= 1) CUDA_OK(cudaStreamWaitEvent(c->xstream, c->rdone[(k - 1) & 3], 0));
         exchange_step(c, k + 1, &plans[(k + 1) % 3], k + 2 < nb ? &plans[(k + 2) % 3] : nullptr);
         CUDA_OK(cudaEventRecord(c->xdone[(k + 1) & 3], c->xstream));
       }
-    }
-    if (sample) {
-      CUDA_OK(cudaEventSynchronize(c->ev[5]));
-      float a = 0, b = 0;
-      CUDA_OK(cudaEventElapsedTime(&a, c->ev[2], c->ev[3]));
-      CUDA_OK(cudaEventElapsedTime(&b, c->ev[4], c->ev[5]));
-      ms_contract += a;
-      ms_reduce += b;
-      sampled++;
+    } else if (p2p && next && next_count > 0) {
+      // prefetch for the next call: the slices of the batch that follows this list in the caller's
+      // tuple list go to the cache now, behind the last batch's compute
+      BatchPlan &pl2 = plans[(k + 1) % 3];
+      if (plan_tuples(next, (size_t)std::min<int64_t>(c->batch, next_count), serial0 + nb, pl2, true)) {
+        c->serial = serial0 + nb + 1;
+        if (k >= 1) CUDA_OK(cudaStreamWaitEvent(c->xstream, c->rdone[(k - 1) & 3], 0));
+        pull_step(c, &pl2);
+      }
     }
   }
   if (nb > 0) CUDA_OK(cudaStreamWaitEvent(c->stream, c->rdone[(nb - 1) & 3], 0));  // the last reduction
@@ -1044,26 +1234,35 @@ void run_list(atrip_b200_ctx *c, const Tuple *list, int64_t count, double *energ
   double tot[2];
   CUDA_OK(cudaMemcpyAsync(tot, c->d_total, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   CUDA_OK(cudaStreamSynchronize(c->stream));
-  if (sh) CUDA_OK(cudaStreamSynchronize(c->xstream));
+  CUDA_OK(cudaStreamSynchronize(c->rstream));
+  if (sh)
+    for (int i = 0; i < NXS; i++) CUDA_OK(cudaStreamSynchronize(c->xs[i]));
+  while (harvested < nb) harvest(harvested++);
   float ms = 0;
   CUDA_OK(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]));
   int64_t real = 0;
   for (int64_t t = 0; t < count; t++) real += !is_fake(list[t]);
   c->timing[0] = ms;
-  c->timing[1] = sampled ? ms_contract / sampled : 0;  // mean ms per sampled contraction launch
-  c->timing[2] = sampled ? ms_reduce / sampled : 0;    // mean ms per sampled reduction (+sum) pair
+  c->timing[1] = nb ? ms_contract / nb : 0;  // mean ms per batch: contraction launch(es) of the V pass
+  c->timing[2] = nb ? ms_reduce / nb : 0;    // mean ms per batch: reduction (+ batch sum) of the V pass
   c->timing[3] = n_contract;
   c->timing[4] = n_reduce;
   c->timing[5] = (double)real;
   c->timing[6] = c->exch_bytes;
   c->timing[7] = c->exch_msgs;
+  c->timing[8] = ms_gap;     // device: sum over batches 1.. of the idle gap in front of the contraction launch
+  c->timing[9] = plan_ms;    // host: building the slot records / fetch schedule
+  c->timing[10] = hits;      // remote slices found in the cache
+  c->timing[11] = misses;    // remote slices fetched
+  c->timing[12] = (double)nb;
   if (energy) *energy = tot[0];
   if (ct_energy) *ct_energy = ct ? tot[1] : tot[0];  // without J the reference's ct_energy == energy
 }
 
 void run_impl(atrip_b200_ctx *c, int64_t first, int64_t count, double *energy, double *ct_energy) {
   REQUIRE(first >= 0 && count >= 0 && (size_t)(first + count) <= c->tuples.size(), "tuple range out of bounds");
-  run_list(c, c->tuples.data() + first, count, energy, ct_energy);
+  const int64_t rest = (int64_t)c->tuples.size() - (first + count);
+  run_list(c, c->tuples.data() + first, count, energy, ct_energy, rest > 0 ? c->tuples.data() + first + count : nullptr, rest);
 }
 
 void set_tuples_impl(atrip_b200_ctx *c) {
@@ -1273,18 +1472,18 @@ int atrip_b200_set_epsilon(atrip_b200_ctx *c, const double *ei, const double *ea
 int atrip_b200_set_Tai(atrip_b200_ctx *c, const double *Tai) {
   return guarded(c, [&] { CUDA_OK(cudaMemcpy(c->Tai, Tai, sizeof(double) * esz(c) * c->No * c->Nv, cudaMemcpyHostToDevice)); });
 }
-int atrip_b200_load_Tabij(atrip_b200_ctx *c, const double *T) { return guarded(c, [&] { c->stores_dirty = true; load_Tabij_impl(c, T); }); }
-int atrip_b200_load_Vabij(atrip_b200_ctx *c, const double *V) { return guarded(c, [&] { c->stores_dirty = true; load_Vabij_impl(c, V); }); }
+int atrip_b200_load_Tabij(atrip_b200_ctx *c, const double *T) { return guarded(c, [&] { begin_store_update(c); load_Tabij_impl(c, T); }); }
+int atrip_b200_load_Vabij(atrip_b200_ctx *c, const double *V) { return guarded(c, [&] { begin_store_update(c); load_Vabij_impl(c, V); }); }
 int atrip_b200_load_Vijka(atrip_b200_ctx *c, const double *V) {
-  return guarded(c, [&] { c->stores_dirty = true; load_hhhp_impl(c, V, c->AX); });
+  return guarded(c, [&] { begin_store_update(c); load_hhhp_impl(c, V, c->AX); });
 }
 int atrip_b200_load_Vabci(atrip_b200_ctx *c, const double *V) {
-  return guarded(c, [&] { c->stores_dirty = true; load_ppph_impl(c, V, c->BY); });
+  return guarded(c, [&] { begin_store_update(c); load_ppph_impl(c, V, c->BY); });
 }
 int atrip_b200_load_Jijka(atrip_b200_ctx *c, const double *V) {
   return guarded(c, [&] {
     REQUIRE(c->cfg.with_J, "context was created without with_J");
-    c->stores_dirty = true;
+    begin_store_update(c);
     load_hhhp_impl(c, V, c->AXJ);
     c->have_J = true;
   });
@@ -1292,7 +1491,7 @@ int atrip_b200_load_Jijka(atrip_b200_ctx *c, const double *V) {
 int atrip_b200_load_Jabci(atrip_b200_ctx *c, const double *V) {
   return guarded(c, [&] {
     REQUIRE(c->cfg.with_J, "context was created without with_J");
-    c->stores_dirty = true;
+    begin_store_update(c);
     load_ppph_impl(c, V, c->BYJ);
     c->have_J = true;
   });
@@ -1339,6 +1538,40 @@ int atrip_b200_tuple_debug(atrip_b200_ctx *c, int64_t a, int64_t b, int64_t cc, 
 int atrip_b200_read_slice(atrip_b200_ctx *c, int32_t kind, int64_t x, int64_t y, double *out) {
   return guarded(c, [&] { read_slice_impl(c, kind, x, y, out); });
 }
+int atrip_b200_upload_slices(atrip_b200_ctx *c, int32_t kind, int64_t n, const int64_t *xy, const double *host) {
+  return guarded(c, [&] { upload_slices_impl(c, kind, n, xy, host); });
+}
+int atrip_b200_upload_slice(atrip_b200_ctx *c, int32_t kind, int64_t x, int64_t y, const double *host) {
+  const int64_t xy[2] = {x, y};
+  return guarded(c, [&] { upload_slices_impl(c, kind, 1, xy, host); });
+}
+int atrip_b200_read_slices(atrip_b200_ctx *c, int32_t kind, int64_t n, const int64_t *xy, double *out) {
+  return guarded(c, [&] { read_slices_impl(c, kind, n, xy, out); });
+}
+// slices of `kind` a rank has to be given (the sources it owns, SliceUnion.cxx:305-332 with
+// RankMap::find, RankMap.cxx:35-85): (x, y) pairs in upload order; returns the count
+int64_t atrip_b200_host_owned_slices(int32_t kind, int64_t Nv, int32_t rank, int32_t nranks, int64_t *xy, int64_t cap) {
+  if (nranks < 1 || Nv < 1 || rank < 0 || rank >= nranks) { g_error = "atrip_b200_host_owned_slices: bad arguments"; return -1; }
+  int64_t k = 0;
+  auto put = [&](int64_t x, int64_t y) {
+    if (xy && k < cap) { xy[2 * k] = x; xy[2 * k + 1] = y; }
+    k++;
+  };
+  if (kind == 100 || kind == 101 || kind == 111) {
+    for (int64_t x = rank; x < Nv; x += nranks) put(x, 0);
+  } else if (kind == 200 || kind == 210) {  // ordered pairs live with their first index
+    for (int64_t x = rank; x < Nv; x += nranks)
+      for (int64_t y = 0; y < Nv; y++) put(x, y);
+  } else if (kind == 201 || kind == 202) {  // x <= y: held by the owner of x and by the owner of y
+    for (int64_t y = 0; y < Nv; y++)
+      for (int64_t x = 0; x <= y; x++)
+        if (x % nranks == rank || y % nranks == rank) put(x, y);
+  } else {
+    g_error = "atrip_b200_host_owned_slices: unknown slice kind";
+    return -1;
+  }
+  return k;
+}
 int atrip_b200_debug_cubes_checksum(atrip_b200_ctx *c, uint64_t *out) {
   return guarded(c, [&] {
     Scratch<unsigned long long> sd(1);
@@ -1355,6 +1588,10 @@ int atrip_b200_debug_cubes_checksum(atrip_b200_ctx *c, uint64_t *out) {
 }
 int atrip_b200_last_timing(const atrip_b200_ctx *c, double *out6) {
   for (int i = 0; i < 6; i++) out6[i] = c->timing[i];
+  return 0;
+}
+int atrip_b200_last_phases(const atrip_b200_ctx *c, double *out6) {
+  for (int i = 0; i < 6; i++) out6[i] = c->timing[8 + i];
   return 0;
 }
 int atrip_b200_last_exchange(const atrip_b200_ctx *c, double *out2) {
@@ -1520,7 +1757,10 @@ int64_t atrip_b200_host_plan_batch(int64_t Nv, int32_t rank, int32_t nranks, con
   std::vector<Tuple> t((size_t)n);
   for (int64_t i = 0; i < n; i++) t[i] = Tuple{abc[3 * i], abc[3 * i + 1], abc[3 * i + 2]};
   BatchPlan pl;
-  plan_batch(m, t.data(), (size_t)n, cache_base3, pl);
+  SliceCache cache;  // empty cache large enough for any batch of n tuples: slots are taken in order 0, 1, ...
+  const int64_t caps[3] = {3 * n + 1, 6 * n + 1, 3 * n + 1};
+  cache.reset(caps);
+  plan_batch(m, t.data(), (size_t)n, cache_base3, cache, 0, pl);
   if (recs) std::memcpy(recs, pl.recs.data(), sizeof(TupleRec) * (size_t)n);
   int64_t k = 0;
   for (int p = 0; p < nranks; p++)
@@ -1532,6 +1772,113 @@ int64_t atrip_b200_host_plan_batch(int64_t Nv, int32_t rank, int32_t nranks, con
       k++;
     }
   return k;
+}
+
+// Walks a whole tuple list in batches through the persistent cache, exactly as run_list does, and
+// checks the invariants the engine relies on with an independent model of the cache contents:
+//   * every cache slot a record addresses holds the slice the tuple needs at that point;
+//   * the copies of batch k never overwrite a slot addressed by batch k or k - 1.
+// calls: number of run calls the list is cut into (each call continues where the last one ended and
+// prefetches the batch behind it, as the P2P transport does).  out[0..5] = slices fetched per kind,
+// hits per kind; out[6] = copy ranges; out[7] = batches.  Returns 0, or -1 with last_error set.
+int atrip_b200_host_check_schedule(int64_t Nv, int32_t rank, int32_t nranks, const uint64_t *abc, int64_t n,
+                                   int64_t batch, int32_t calls, const int64_t *cap3, double *out8) {
+  if (nranks < 1 || Nv < 1 || rank < 0 || rank >= nranks || n < 0 || batch < 1 || calls < 1) {
+    g_error = "atrip_b200_host_check_schedule: bad arguments";
+    return -1;
+  }
+  const ShardMap m(Nv, nranks, rank);
+  std::vector<Tuple> t((size_t)n);
+  for (int64_t i = 0; i < n; i++) t[i] = Tuple{abc[3 * i], abc[3 * i + 1], abc[3 * i + 2]};
+  int64_t owned[3];
+  for (int k = 0; k < 3; k++) owned[k] = m.owned(k, rank);
+  SliceCache cache;
+  cache.reset(cap3);
+  // model: what each cache slot holds (peer, owner slot), and the last batch that addressed it
+  std::vector<uint64_t> holds[3];
+  std::vector<int64_t> used_by[3];
+  for (int k = 0; k < 3; k++) {
+    holds[k].assign((size_t)cap3[k], ~0ull);
+    used_by[k].assign((size_t)cap3[k], INT64_MIN / 2);
+  }
+  double stats[8] = {0};
+  int64_t serial = 0;
+  BatchPlan pl;
+  auto fail = [&](const std::string &msg) {
+    g_error = "schedule check: " + msg;
+    return -1;
+  };
+  auto apply = [&](const BatchPlan &p, int64_t ser) -> int {  // the copies of a batch
+    for (int peer = 0; peer < nranks; peer++)
+      for (const FetchRange &fr : p.fetch[(size_t)peer]) {
+        stats[6] += 1;
+        for (int64_t q = 0; q < fr.count; q++) {
+          const int64_t s = fr.dst_slot + q;
+          if (s < 0 || s >= cap3[fr.kind]) return fail("copy outside the cache");
+          if (used_by[fr.kind][(size_t)s] >= ser - 1) return fail("copy overwrites a slot of a batch that may still compute");
+          holds[fr.kind][(size_t)s] = ((uint64_t)peer << 48) | (uint64_t)(fr.src_slot + q);
+        }
+      }
+    return 0;
+  };
+  auto verify = [&](const BatchPlan &p, const Tuple *tp, size_t nt, int64_t ser) -> int {
+    for (size_t i = 0; i < nt; i++) {
+      const TupleRec &r = p.recs[i];
+      if (r.fake) continue;
+      const int64_t x[3] = {(int64_t)tp[i][0], (int64_t)tp[i][1], (int64_t)tp[i][2]};
+      auto check = [&](int kind, int slot, int owner, int64_t oslot) -> int {
+        if (owner == rank) return slot == oslot ? 0 : 1;
+        const int64_t cs = slot - owned[kind];
+        if (cs < 0 || cs >= cap3[kind]) return 1;
+        if (holds[kind][(size_t)cs] != (((uint64_t)owner << 48) | (uint64_t)oslot)) return 1;
+        used_by[kind][(size_t)cs] = ser;
+        return 0;
+      };
+      int bad = 0;
+      for (int k = 0; k < 3; k++) bad += check(KA, r.ax[k], m.ownerA(x[k]), m.slotA(x[k]));
+      const int64_t yz[6][3] = {{x[1], x[2], 0}, {x[0], x[2], 0}, {x[2], x[1], 1}, {x[0], x[1], 0}, {x[2], x[0], 1}, {x[1], x[0], 1}};
+      for (int k = 0; k < 6; k++) {
+        const int64_t id = m.idB(yz[k][0], yz[k][1], yz[k][2] != 0);
+        bad += check(KB, r.by[k], m.ownerB(id), m.slotB(id));
+      }
+      const int64_t vp[3][2] = {{x[1], x[2]}, {x[0], x[2]}, {x[0], x[1]}};
+      for (int k = 0; k < 3; k++) {
+        const int64_t ls = m.localV(vp[k][0], vp[k][1]);
+        if (ls >= 0) bad += (r.vij[k] != ls);
+        else bad += check(KV, r.vij[k], m.ownerV(vp[k][0] + vp[k][1] * Nv), m.slotV1(vp[k][0], vp[k][1]));
+      }
+      if (bad) return fail("a record addresses a slot that does not hold its slice (tuple " + std::to_string(i) + " of batch " + std::to_string(ser) + ")");
+    }
+    return 0;
+  };
+  const int64_t per_call = (n + calls - 1) / calls;
+  for (int64_t first = 0; first < n; first += per_call) {
+    const int64_t count = std::min(per_call, n - first);
+    serial += 2;  // run_list: everything of the previous call has completed
+    const int64_t nb = (count + batch - 1) / batch;
+    for (int64_t k = 0; k < nb; k++) {
+      const Tuple *tp = t.data() + first + k * batch;
+      const size_t nt = (size_t)std::min<int64_t>(batch, count - k * batch);
+      plan_batch(m, tp, nt, owned, cache, serial + k, pl);
+      if (pl.overflow) return fail("cache overflow");
+      for (int q = 0; q < 3; q++) { stats[q] += (double)pl.used[q]; stats[3 + q] += (double)pl.hits[q]; }
+      if (apply(pl, serial + k) || verify(pl, tp, nt, serial + k)) return -1;
+      stats[7] += 1;
+    }
+    serial += nb;
+    const int64_t rest = n - (first + count);
+    if (rest > 0) {  // prefetch for the next call
+      plan_batch(m, t.data() + first + count, (size_t)std::min(batch, rest), owned, cache, serial, pl);
+      if (pl.overflow) cache.invalidate();
+      else {
+        for (int q = 0; q < 3; q++) stats[q] += (double)pl.used[q];
+        if (apply(pl, serial)) return -1;
+        serial += 1;
+      }
+    }
+  }
+  if (out8) std::memcpy(out8, stats, sizeof(stats));
+  return 0;
 }
 int atrip_b200_host_cache_need(int64_t Nv, int32_t rank, int32_t nranks, const uint64_t *abc, int64_t n,
                                int64_t batch, int64_t *out3) {

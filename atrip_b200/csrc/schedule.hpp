@@ -10,7 +10,8 @@
 //   the per-tuple MPI_Allgather of the slice database (Atrip.cxx:443-453) + send/receive
 //   (SliceUnion.cxx:365-505)                              -> one request list per peer per BATCH of
 //                                                            tuples, contiguous slot ranges merged
-//   clear_unused_slices_for_next_tuple (SliceUnion.cxx:173-290) -> two cache regions used alternately
+//   clear_unused_slices_for_next_tuple (SliceUnion.cxx:173-290) -> SliceCache: slots re-assigned in
+//                                                            ring order once two batches old
 //
 // Ownership (DESIGN.md "Multi-GPU"):
 //   A  slices (TAPHH+HHHA of x)                      owner x % n               (RankMap.cxx:43-82)
@@ -23,7 +24,9 @@
 // tuples (p0, p1, z = home, home + n, ...) merge into one range per (p0, .) / (p1, .) row.
 #pragma once
 #include <algorithm>
+#include <climits>
 #include <cstdint>
+#include <utility>
 #include <vector>
 
 #include "tuples.hpp"
@@ -89,7 +92,7 @@ struct ShardMap {
 };
 
 // contiguous slots [src_slot, src_slot + count) of `kind` at the owner -> cache slots
-// [dst_slot, dst_slot + count) (relative to the batch's cache region) at the requester
+// [dst_slot, dst_slot + count) of the requester's fetch cache of that kind
 struct FetchRange {
   int kind;
   int64_t src_slot;
@@ -100,24 +103,126 @@ struct FetchRange {
 struct BatchPlan {
   std::vector<TupleRec> recs;
   std::vector<std::vector<FetchRange>> fetch;  // [peer]
-  int64_t used[3] = {0, 0, 0};                 // cache slots taken per kind
+  int64_t used[3] = {0, 0, 0};                 // slices fetched for this batch per kind (cache misses)
+  int64_t hits[3] = {0, 0, 0};                 // remote slices found in the cache (fetched for an earlier batch)
+  bool overflow = false;                       // the cache had no free slot left: capacity too small
 };
 
 inline bool is_fake(const Tuple &t) { return t[0] == 0 && t[1] == 0 && t[2] == 0; }
 
-// Slots for the tuples t[0..n) on rank m.me.  cache_base[kind] = slot number the batch's cache
-// region starts at (>= owned count).  Slices already requested by an earlier tuple of the batch
-// are reused (the reference's "Recycled"/exact-match cases, SliceUnion.cxx:66-137).
-inline void plan_batch(const ShardMap &m, const Tuple *t, size_t n, const int64_t cache_base[3], BatchPlan &out) {
+// Fetch cache of one rank: cap[kind] slots per store, shared by all batches of all runs.  Plays the
+// role of the reference's slice buffers with their Recycled / exact-match reuse and of
+// clear_unused_slices_for_next_tuple (SliceUnion.cxx:66-137, 173-290), at batch granularity:
+//   * a remote slice stays addressable (key -> slot) until its slot is handed to another slice, so
+//     a batch re-uses what earlier batches fetched (the two slowly varying indices of a group-and-
+//     sort run keep their A slices for the whole run);
+//   * a slot may be re-assigned while planning batch `serial` only if the last batch that addressed
+//     it has serial <= serial - 2: batch serial - 1 may still be computing when the copies of batch
+//     `serial` are in flight (the engine orders the copies behind the reduction of serial - 2);
+//   * free slots are taken in ring order, so the misses of a batch, sorted by owner slot, mostly
+//     land in consecutive slots and merge into few copies.
+struct SliceCache {
+  static constexpr uint64_t EMPTY = ~0ull;
+  int64_t cap[3] = {0, 0, 0};
+  std::vector<uint64_t> key[3];   // slot -> slice held
+  std::vector<int64_t> last[3];   // slot -> serial of the last batch that addressed it
+  std::vector<std::pair<uint64_t, int32_t>> table[3];  // open-addressing hash: key -> slot
+  int64_t hand[3] = {0, 0, 0};
+  size_t touched[3] = {0, 0, 0};  // table entries that are not "never used" any more (live + tombstones)
+
+  void reset(const int64_t cap_[3]) {
+    for (int k = 0; k < 3; k++) {
+      cap[k] = cap_[k];
+      key[k].assign((size_t)cap[k], EMPTY);
+      last[k].assign((size_t)cap[k], INT64_MIN / 2);
+      size_t n = 16;
+      while (n < 4 * (size_t)cap[k]) n <<= 1;
+      table[k].assign(n, {EMPTY, -1});
+      hand[k] = 0;
+      touched[k] = 0;
+    }
+  }
+  // the stores behind the cached copies changed: forget every slice, keep the capacity
+  void invalidate() { reset(cap); }
+
+  static size_t hash(uint64_t k) {
+    k ^= k >> 33;
+    k *= 0xff51afd7ed558ccdull;
+    k ^= k >> 29;
+    return (size_t)k;
+  }
+  int64_t find(int kind, uint64_t k) const {
+    const auto &t = table[kind];
+    for (size_t i = hash(k) & (t.size() - 1);; i = (i + 1) & (t.size() - 1)) {
+      if (t[i].first == k) return t[i].second;
+      if (t[i].first == EMPTY && t[i].second == -1) return -1;  // never used: end of the probe chain
+    }
+  }
+  void insert(int kind, uint64_t k, int32_t slot) {
+    auto &t = table[kind];
+    for (size_t i = hash(k) & (t.size() - 1);; i = (i + 1) & (t.size() - 1))
+      if (t[i].first == EMPTY) {  // never used or tombstone
+        if (t[i].second == -1) touched[kind]++;
+        t[i] = {k, slot};
+        return;
+      }
+  }
+  void erase(int kind, uint64_t k) {
+    auto &t = table[kind];
+    for (size_t i = hash(k) & (t.size() - 1);; i = (i + 1) & (t.size() - 1)) {
+      if (t[i].first == k) {
+        t[i] = {EMPTY, -2};  // tombstone: keeps the probe chain intact
+        return;
+      }
+      if (t[i].first == EMPTY && t[i].second == -1) return;
+    }
+  }
+  // a free slot for a new slice of batch `serial` (-1: none; the cache is too small)
+  int64_t take(int kind, uint64_t k, int64_t serial) {
+    const int64_t n = cap[kind];
+    for (int64_t step = 0; step < n; step++) {
+      const int64_t s = hand[kind];
+      hand[kind] = s + 1 == n ? 0 : s + 1;
+      if (last[kind][(size_t)s] <= serial - 2) {
+        if (key[kind][(size_t)s] != EMPTY) erase(kind, key[kind][(size_t)s]);
+        key[kind][(size_t)s] = k;
+        last[kind][(size_t)s] = serial;
+        insert(kind, k, (int32_t)s);
+        if (2 * touched[kind] > table[kind].size()) compact(kind);
+        return s;
+      }
+    }
+    return -1;
+  }
+  // tombstones accumulate (every re-assigned slot leaves one): rebuild the table before the probe
+  // chains run out of never-used entries
+  void compact(int kind) {
+    auto &t = table[kind];
+    for (auto &e : t) e = {EMPTY, -1};
+    touched[kind] = 0;
+    for (int64_t s = 0; s < cap[kind]; s++)
+      if (key[kind][(size_t)s] != EMPTY) insert(kind, key[kind][(size_t)s], (int32_t)s);
+  }
+};
+
+// Slots for the tuples t[0..n) on rank m.me, batch number `serial`.  owned[kind] = owned slot count
+// of the store (cache slot s is addressed as owned + s).  Remote slices already in the cache --
+// fetched for an earlier tuple of this batch or for an earlier batch -- are reused (the reference's
+// "Recycled"/exact-match cases, SliceUnion.cxx:66-137); the rest become fetch ranges.
+inline void plan_batch(const ShardMap &m, const Tuple *t, size_t n, const int64_t owned[3], SliceCache &cache,
+                       int64_t serial, BatchPlan &out) {
   struct Need {
     uint64_t key;
     uint32_t rec, field;
   };
   static thread_local std::vector<Need> needs;
+  static thread_local std::vector<std::pair<size_t, size_t>> misses;  // [first, last) runs of `needs` with one key
   needs.clear();
+  misses.clear();
   out.recs.resize(n);
   out.fetch.assign((size_t)m.n, {});
-  out.used[0] = out.used[1] = out.used[2] = 0;
+  for (int k = 0; k < 3; k++) out.used[k] = out.hits[k] = 0;
+  out.overflow = false;
   const int64_t Nv = m.Nv;
   auto remote = [&](int peer, int kind, int64_t slot, size_t rec, int field) {
     needs.push_back(Need{((uint64_t)peer << 48) | ((uint64_t)kind << 44) | (uint64_t)slot, (uint32_t)rec, (uint32_t)field});
@@ -155,19 +260,43 @@ inline void plan_batch(const ShardMap &m, const Tuple *t, size_t n, const int64_
   }
   if (needs.empty()) return;
   std::sort(needs.begin(), needs.end(), [](const Need &x, const Need &y) { return x.key < y.key; });
-  uint64_t prev = ~0ull;
-  int64_t dst = 0;
-  for (const Need &nd : needs) {
-    const int peer = (int)(nd.key >> 48), kind = (int)((nd.key >> 44) & 15);
-    const int64_t slot = (int64_t)(nd.key & ((1ull << 44) - 1));
-    if (nd.key != prev) {
-      dst = out.used[kind]++;
-      auto &fr = out.fetch[(size_t)peer];
-      if (!fr.empty() && fr.back().kind == kind && fr.back().src_slot + fr.back().count == slot) fr.back().count++;
-      else fr.push_back(FetchRange{kind, slot, 1, dst});
-      prev = nd.key;
+  auto kind_of = [](uint64_t key) { return (int)((key >> 44) & 15); };
+  auto assign = [&](size_t lo, size_t hi, int kind, int64_t slot) {
+    for (size_t q = lo; q < hi; q++) reinterpret_cast<int *>(&out.recs[needs[q].rec])[needs[q].field] = (int)(owned[kind] + slot);
+  };
+  // pass 1: hits keep their slot (and are marked in use before any slot is re-assigned)
+  for (size_t lo = 0; lo < needs.size();) {
+    size_t hi = lo + 1;
+    while (hi < needs.size() && needs[hi].key == needs[lo].key) hi++;
+    const int kind = kind_of(needs[lo].key);
+    const int64_t s = cache.find(kind, needs[lo].key);
+    if (s >= 0) {
+      cache.last[kind][(size_t)s] = serial;
+      out.hits[kind]++;
+      assign(lo, hi, kind, s);
+    } else {
+      misses.push_back({lo, hi});
     }
-    reinterpret_cast<int *>(&out.recs[nd.rec])[nd.field] = (int)(cache_base[kind] + dst);
+    lo = hi;
+  }
+  // pass 2: misses take free slots in ring order, in owner-slot order, and merge into ranges
+  for (const auto &mr : misses) {
+    const uint64_t key = needs[mr.first].key;
+    const int peer = (int)(key >> 48), kind = kind_of(key);
+    const int64_t src = (int64_t)(key & ((1ull << 44) - 1));
+    const int64_t s = cache.take(kind, key, serial);
+    if (s < 0) {
+      out.overflow = true;
+      return;
+    }
+    out.used[kind]++;
+    auto &fr = out.fetch[(size_t)peer];
+    if (!fr.empty() && fr.back().kind == kind && fr.back().src_slot + fr.back().count == src &&
+        fr.back().dst_slot + fr.back().count == s)
+      fr.back().count++;
+    else
+      fr.push_back(FetchRange{kind, src, 1, s});
+    assign(mr.first, mr.second, kind, s);
   }
 }
 

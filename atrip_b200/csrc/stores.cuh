@@ -431,6 +431,141 @@ __global__ void read_slice_z_kernel(int kind, StoreDims d, const double *AXx, co
   }
 }
 
+
+// ------------------------------------------------------------------ per-slice ingest / read-back
+// The reference's SliceUnion<F>::init slices, per rank, only the sources that rank owns
+// (SliceUnion.cxx:305-332, Unions.hpp:21-75) and keeps them as contiguous buffers in the slice
+// layout CTF::slice yields.  upload_slices_kernel takes a chunk of such buffers (n slices of one
+// kind, back to back) and writes them into the stores; slices this rank does not hold are skipped.
+//   kind 100 TA(x)      [E + Nv (p + q No)]      = Tabij[x,E,p,q]   -> AX particle part
+//        101 VIJKA(x)   [i + j No + k No^2]      = Vijka[i,j,k,x]   -> AX hole part (sign, (p,q) swap)
+//        200 VABCI(x,y) [E + Nv r]               = Vabci[x,y,E,r]   -> BY particle part (+ diagonal twin)
+//        201 TABIJ(x,y) [p + q No], x <= y       = Tabij[x,y,p,q]   -> BY hole part of (x,y) and of (y,x)'
+//        202 VABIJ(x,y) [i + j No], x <= y       = Vabij[x,y,i,j]   -> VIJ
+// Z = complex field: source elements are interleaved (re, im), stores as in "complex field" above.
+struct SliceTables {
+  const int *xtab, *btab, *vtab;  // global id -> owned slot or -1
+};
+
+template <bool Z>
+__device__ __forceinline__ void put_A(double *AX, const StoreDims &d, size_t slot, size_t m, size_t kk, double re, double im) {
+  const size_t No = d.No, Kp = d.Kp;
+  if (!Z) {
+    AX[(slot * No * No + m) * Kp + kk] = re;
+  } else {
+    const size_t Kh = (size_t)d.No + d.Nv;
+    double *row0 = AX + ((slot * 2 + 0) * No * No + m) * Kp, *row1 = AX + ((slot * 2 + 1) * No * No + m) * Kp;
+    row0[kk] = re;
+    row0[Kh + kk] = -im;
+    row1[kk] = im;
+    row1[Kh + kk] = re;
+  }
+}
+template <bool Z>
+__device__ __forceinline__ void put_B(double *BY, const StoreDims &d, size_t slot, size_t r, size_t kk, double re, double im) {
+  double *row = BY + (slot * d.No + r) * d.Kp;
+  row[kk] = re;
+  if (Z) row[(size_t)d.No + d.Nv + kk] = im;
+}
+
+template <bool Z>
+__global__ void upload_slices_kernel(int kind, const double *src, const long long *xy, int n, StoreDims d, SliceTables tb,
+                                     double *AX, double *BY, double *VIJ) {
+  const size_t No = d.No, Nv = d.Nv;
+  const size_t per = kind == 100 ? Nv * No * No : (kind == 101 ? No * No * No : (kind == 200 ? Nv * No : No * No));
+  const size_t total = per * (size_t)n;
+  for (size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x; g < total; g += (size_t)gridDim.x * blockDim.x) {
+    const size_t s = g / per, e = g - s * per;
+    const long long x = xy[2 * s], y = xy[2 * s + 1];
+    if (kind == 101) {
+      // destination-friendly enumeration (L fastest): AX[m = p + q No][Nv + L] = -conj(Vijka[q,p,L,x])
+      const int slot = tb.xtab[x];
+      if (slot < 0) continue;
+      const size_t L = e % No, m = e / No, p = m % No, q = m / No;
+      const size_t si = s * per + q + p * No + L * No * No;
+      const double re = Z ? src[2 * si] : src[si], im = Z ? src[2 * si + 1] : 0.0;
+      put_A<Z>(AX, d, (size_t)slot, m, Nv + L, -re, im);
+      continue;
+    }
+    const double re = Z ? src[2 * g] : src[g], im = Z ? src[2 * g + 1] : 0.0;
+    if (kind == 100) {
+      const int slot = tb.xtab[x];
+      if (slot >= 0) put_A<Z>(AX, d, (size_t)slot, e / Nv, e % Nv, re, im);
+    } else if (kind == 200) {
+      const size_t E = e % Nv, r = e / Nv;
+      const int s1 = tb.btab[x + y * (long long)Nv];
+      if (s1 >= 0) put_B<Z>(BY, d, (size_t)s1, r, E, re, im);
+      if (x == y) {
+        const int s2 = tb.btab[Nv * Nv + x];
+        if (s2 >= 0) put_B<Z>(BY, d, (size_t)s2, r, E, re, im);
+      }
+    } else if (kind == 201) {
+      const size_t p = e % No, q = e / No;
+      const int s1 = tb.btab[x + y * (long long)Nv];  // (x,y): hole[r = q][L = p]
+      if (s1 >= 0) put_B<Z>(BY, d, (size_t)s1, q, Nv + p, re, im);
+      const int s2 = tb.btab[x == y ? (long long)(Nv * Nv) + x : y + x * (long long)Nv];  // (y,x)': hole[r = p][L = q]
+      if (s2 >= 0) put_B<Z>(BY, d, (size_t)s2, p, Nv + q, re, im);
+    } else {  // 202
+      const int slot = tb.vtab[x + y * (long long)Nv];
+      if (slot >= 0) {
+        if (Z) {
+          VIJ[2 * ((size_t)slot * No * No + e)] = re;
+          VIJ[2 * ((size_t)slot * No * No + e) + 1] = im;
+        } else {
+          VIJ[(size_t)slot * No * No + e] = re;
+        }
+      }
+    }
+  }
+}
+
+// n slices of one kind back to the reference's slice layout (the inverse of the above); a slice
+// this rank does not hold comes back as NaN.  TABIJ(x,y) is read from the TA(x) rows (kind 201
+// therefore needs x owned), as read_slice_kernel does.
+template <bool Z>
+__global__ void read_slices_kernel(int kind, double *out, const long long *xy, int n, StoreDims d, SliceTables tb,
+                                   const double *AX, const double *BY, const double *VIJ) {
+  const size_t No = d.No, Nv = d.Nv, Kp = d.Kp, Kh = No + Nv;
+  const size_t per = kind == 100 ? Nv * No * No : (kind == 101 ? No * No * No : (kind == 200 ? Nv * No : No * No));
+  const size_t total = per * (size_t)n;
+  const double nan = __longlong_as_double(0x7ff8000000000000ll);
+  for (size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x; g < total; g += (size_t)gridDim.x * blockDim.x) {
+    const size_t s = g / per, e = g - s * per;
+    const long long x = xy[2 * s], y = xy[2 * s + 1];
+    double re = nan, im = nan;
+    if (kind == 100 || kind == 101 || kind == 201) {
+      const int slot = tb.xtab[x];
+      if (slot >= 0) {
+        const double *A = AX + (size_t)slot * (Z ? 2 : 1) * No * No * Kp;  // variant 0 rows: [Re A | -Im A]
+        size_t m, kk;
+        double sg = 1.0;
+        if (kind == 100) { m = e / Nv; kk = e % Nv; }
+        else if (kind == 201) { m = e; kk = (size_t)y; }
+        else { const size_t p = e % No, q = (e / No) % No, L = e / (No * No); m = q + p * No; kk = Nv + L; sg = -1.0; }
+        re = sg * A[m * Kp + kk];
+        // hole part holds -conj(H): Re A = -Re H, Im A = +Im H; plane 1 of variant 0 holds -Im A
+        if (Z) im = -A[m * Kp + Kh + kk];
+      }
+    } else if (kind == 200) {
+      const int slot = tb.btab[x + y * (long long)Nv];
+      if (slot >= 0) {
+        const size_t E = e % Nv, r = e / Nv;
+        const double *row = BY + ((size_t)slot * No + r) * Kp;
+        re = row[E];
+        if (Z) im = row[Kh + E];
+      }
+    } else {
+      const int slot = tb.vtab[x + y * (long long)Nv];
+      if (slot >= 0) {
+        re = Z ? VIJ[2 * ((size_t)slot * No * No + e)] : VIJ[(size_t)slot * No * No + e];
+        if (Z) im = VIJ[2 * ((size_t)slot * No * No + e) + 1];
+      }
+    }
+    if (Z) { out[2 * g] = re; out[2 * g + 1] = im; }
+    else out[g] = re;
+  }
+}
+
 // ------------------------------------------------------------------ read back in reference layout
 // kind: 100 TA(x), 101 VIJKA(x), 200 VABCI(x,y), 201 TABIJ(x,y), 202 VABIJ(x,y)
 __global__ void read_slice_kernel(int kind, StoreDims d, const double *AXx, const double *BYxy, const double *VIJxy,

@@ -76,6 +76,32 @@ int atrip_b200_load_Vabci(atrip_b200_ctx *ctx, const double *Vabci /* [Nv,Nv,Nv,
 int atrip_b200_load_Jijka(atrip_b200_ctx *ctx, const double *Jijka /* [No,No,No,Nv] */);
 int atrip_b200_load_Jabci(atrip_b200_ctx *ctx, const double *Jabci /* [Nv,Nv,Nv,No] */);
 
+/* ---- sliced tensors, one slice at a time: what SliceUnion<F>::init does per rank (SliceUnion.cxx:305-332:
+ *      for every source this rank owns, RankMap::find RankMap.cxx:35-85, CTF::slice it into a contiguous
+ *      buffer, slice_into_vector Unions.hpp:21-75).  `host` holds n slices of one kind back to back in the
+ *      REFERENCE's slice layout (column-major, what CTF::slice yields), xy their (x, y) indices (y ignored
+ *      for the single-index kinds).  A rank uploads the slices atrip_b200_host_owned_slices lists for it
+ *      and never needs the full tensors; slices the rank does not hold are skipped.  Kinds (Slice.hpp:99-108
+ *      names):
+ *        100 TA(x)      [Nv,No,No] = Tabij[x,:,:,:]   (TAPHH, Unions.hpp:77-113)
+ *        101 VIJKA(x)   [No,No,No] = Vijka[:,:,:,x]   (HHHA,  Unions.hpp:115-152)      111 the same of Jijka
+ *        200 VABCI(x,y) [Nv,No]    = Vabci[x,y,:,:]   (ABPH,  Unions.hpp:154-197)      210 the same of Jabci
+ *        201 TABIJ(x,y) [No,No]    = Tabij[x,y,:,:], x <= y  (TABHH, Unions.hpp:239-278)
+ *        202 VABIJ(x,y) [No,No]    = Vabij[x,y,:,:], x <= y  (ABHH,  Unions.hpp:199-237)
+ *      Returns when the host buffer has been consumed.  With sharded stores and transport 2 the first
+ *      upload after a run is collective (a peer may still be reading this rank's stores). */
+int atrip_b200_upload_slices(atrip_b200_ctx *ctx, int32_t kind, int64_t n, const int64_t *xy /* n x 2 */,
+                             const double *host);
+int atrip_b200_upload_slice(atrip_b200_ctx *ctx, int32_t kind, int64_t x, int64_t y, const double *host);
+/*      the inverse, for parity tests and for building host-side shards: n slices of one kind back to the
+ *      reference layout; a slice this rank does not hold comes back as NaN (kind 201 reads the TA(x) rows,
+ *      so it needs x owned) */
+int atrip_b200_read_slices(atrip_b200_ctx *ctx, int32_t kind, int64_t n, const int64_t *xy, double *out);
+/*      host-only: the (x, y) list of the slices of `kind` rank `rank` of `nranks` has to be given; returns
+ *      the count and writes at most cap pairs (xy may be NULL to query the count) */
+int64_t atrip_b200_host_owned_slices(int32_t kind, int64_t Nv, int32_t rank, int32_t nranks, int64_t *xy,
+                                     int64_t cap);
+
 /* ---- synthetic inputs generated on the device from the counter-based generator
  *      value = f(seed, tensor id, column-major linear index) (DESIGN.md "Synthetic inputs";
  *      plays the role of CTF fill_random in bench/main.cxx:54-89, with ranges that keep the
@@ -138,6 +164,14 @@ int atrip_b200_debug_cubes_checksum(atrip_b200_ctx *ctx, uint64_t *out);
  *      out[5] = non-fake tuples processed */
 int atrip_b200_last_timing(const atrip_b200_ctx *ctx, double *out6);
 
+/*      phases of the last atrip_b200_run: out[0] = ms the compute stream sat idle in front of contraction
+ *      launches of batches 1.. (slice fetch not landed / cube buffer not yet reduced; device events),
+ *      out[1] = host ms spent building slot records and fetch schedules (replaces build_local_database,
+ *      SliceUnion.cxx:36-171), out[2] = remote slices found in the fetch cache (the reference's Recycled /
+ *      exact-match cases, SliceUnion.cxx:66-137), out[3] = remote slices fetched, out[4] = batches,
+ *      out[5] = ms of idle gap in front of batch 0 (start-up of the call) */
+int atrip_b200_last_phases(const atrip_b200_ctx *ctx, double *out6);
+
 /* ---- derived constants the caller needs for reporting */
 int64_t atrip_b200_kp(const atrip_b200_ctx *ctx);            /* padded contraction length */
 double atrip_b200_flops_per_tuple(const atrip_b200_ctx *ctx); /* 12 No^3 (No+Nv), x4 complex; Atrip.cxx:578-580 */
@@ -183,11 +217,19 @@ int atrip_b200_host_shard_sizes(int64_t Nv, int32_t rank, int32_t nranks, int64_
  *      and the per-tuple database exchange, Atrip.cxx:414-459): for the n tuples abc of `rank`
  *      writes recs (n x 16 int32: a b c fake, AX slots of a b c, BY slots of (b,c) (a,c) (c,b)'
  *      (a,b) (c,a)' (b,a)', VIJ slots of (b,c) (a,c) (a,b); slots >= owned count address the cache,
- *      cache_base3 = first slot of the batch's cache region per store) and up to cap fetch ranges
- *      (5 x int64 each: peer, store 0/1/2, first slot at the owner, count, first cache slot
- *      relative to the region).  Returns the number of ranges, < 0 on error. */
+ *      cache_base3 = slot number of cache slot 0 per store = owned count) and up to cap fetch ranges
+ *      (5 x int64 each: peer, store 0/1/2, first slot at the owner, count, first cache slot;
+ *      planned against an EMPTY fetch cache, so cache slots count up from 0).  Returns the number of
+ *      ranges, < 0 on error. */
 int64_t atrip_b200_host_plan_batch(int64_t Nv, int32_t rank, int32_t nranks, const uint64_t *abc, int64_t n,
                                    const int64_t *cache_base3, int32_t *recs, int64_t *ranges, int64_t cap);
+/*      the whole list cut into `calls` run calls and walked batch by batch through the persistent fetch
+ *      cache (cap3 slots per store) exactly as atrip_b200_run does, checked against an independent model
+ *      of the cache contents: every record addresses a slot that holds its slice, no copy overwrites a
+ *      slot of a batch that may still compute.  out[0..2] slices fetched per store, out[3..5] cache hits,
+ *      out[6] copy ranges, out[7] batches.  Returns 0, or -1 with the violation in last_error. */
+int atrip_b200_host_check_schedule(int64_t Nv, int32_t rank, int32_t nranks, const uint64_t *abc, int64_t n,
+                                   int64_t batch, int32_t calls, const int64_t *cap3, double *out8);
 /*      cache slots per store that any window of `batch` consecutive tuples of the list needs */
 int atrip_b200_host_cache_need(int64_t Nv, int32_t rank, int32_t nranks, const uint64_t *abc, int64_t n,
                                int64_t batch, int64_t *out3);

@@ -137,3 +137,66 @@ def test_remote_fetches_per_tuple_match_survey(lib):
             tot[kind] += ranges[ranges[:, 1] == kind][:, 3].sum()
     per_tuple = tot / len(tl)
     assert per_tuple[KB] < 2.6 and per_tuple[KA] < 0.5 and per_tuple[KV] < 0.3, per_tuple
+
+
+def _caps(need):
+    return [max(3 * need[KA], 3), max(3 * need[KB], 6), max(3 * need[KV], 3)]
+
+
+@pytest.mark.parametrize("Nv,n,batch,calls", [(16, 2, 7, 1), (13, 3, 5, 4), (24, 4, 16, 3), (17, 8, 3, 5), (40, 8, 24, 2),
+                                              (12, 1, 10, 2)])
+def test_persistent_cache_schedule_is_consistent(lib, Nv, n, batch, calls):
+    """the engine's real schedule (atrip_b200_run: one fetch cache shared by all batches and calls, slots
+    re-assigned in ring order two batches after their last use, prefetch for the next call) checked
+    against an independent model of the cache contents, for every rank"""
+    for r in range(n):
+        tl = capi.host_tuples(capi.GROUP_AND_SORT, Nv, r, n, pad=True)
+        need = capi.cache_need(Nv, r, n, tl, batch)
+        st = capi.check_schedule(Nv, r, n, tl, batch, _caps(need), calls=calls)
+        assert st["batches"] == sum(-(-len(c) // batch) for c in np.array_split(tl, range(-(-len(tl) // calls), len(tl), -(-len(tl) // calls))))
+        if n == 1:
+            assert st["fetched"] == [0, 0, 0] and st["hits"] == [0, 0, 0]
+
+
+def test_cache_reuse_cuts_the_single_index_traffic(lib):
+    """the two slowly varying indices of a group-and-sort run keep their A slices across batches
+    (the reference's Recycled / exact-match reuse, SliceUnion.cxx:66-137): with the persistent cache
+    an A slice is fetched far less often than once per batch"""
+    Nv, n, r, batch = 64, 8, 3, 8
+    tl = capi.host_tuples(capi.GROUP_AND_SORT, Nv, r, n, pad=False)
+    owned = capi.shard_sizes(Nv, r, n)
+    per_batch = 0
+    for k0 in range(0, len(tl), batch):
+        _, ranges = capi.plan_batch(Nv, r, n, tl[k0:k0 + batch], owned)
+        per_batch += int(ranges[ranges[:, 1] == KA][:, 3].sum())
+    need = capi.cache_need(Nv, r, n, tl, batch)
+    st = capi.check_schedule(Nv, r, n, tl, batch, _caps(need))
+    assert st["fetched"][KA] < 0.6 * per_batch, (st, per_batch)
+    assert st["hits"][KA] > 0
+
+
+def test_too_small_a_cache_is_reported(lib):
+    Nv, n, r, batch = 24, 4, 1, 16
+    tl = capi.host_tuples(capi.GROUP_AND_SORT, Nv, r, n, pad=True)
+    with pytest.raises(capi.EngineError, match="overflow"):
+        capi.check_schedule(Nv, r, n, tl, batch, [1, 2, 1])
+
+
+def test_owned_slice_lists_cover_every_slice_once_per_holder(lib):
+    """atrip_b200_host_owned_slices (what a rank has to upload, SliceUnion.cxx:305-332) against the
+    ownership map: single-index and ordered-pair slices have one holder, x <= y pair slices are held by
+    the owners of both indices"""
+    Nv, n = 13, 3
+    seen = {k: {} for k in (capi.TA, capi.VIJKA, capi.VABCI, capi.TABIJ, capi.VABIJ)}
+    for r in range(n):
+        for kind in seen:
+            for x, y in capi.owned_slices(kind, Nv, r, n).tolist():
+                seen[kind].setdefault((x, y), set()).add(r)
+    for x in range(Nv):
+        assert seen[capi.TA][(x, 0)] == {x % n} and seen[capi.VIJKA][(x, 0)] == {x % n}
+        for y in range(Nv):
+            assert seen[capi.VABCI][(x, y)] == {x % n}
+            if x <= y:
+                assert seen[capi.TABIJ][(x, y)] == {x % n, y % n}
+                assert seen[capi.VABIJ][(x, y)] == {x % n, y % n}
+    assert len(seen[capi.VABCI]) == Nv * Nv and len(seen[capi.TABIJ]) == Nv * (Nv + 1) // 2

@@ -2,12 +2,15 @@
 
 A consumer warp may hand a ring stage back to the producer (mbarrier arrive on the stage's "empty"
 barrier, SASS `SYNCS.ARRIVE.TRANS64.A1T0`) only after every LDS of that stage has delivered its data.
-The source orders  fragment loads + DMMAs -> __syncwarp() -> arrive,  but ptxas is free to move the
-arrive (no register dependency) and the WARPSYNC inside a basic block: in a straight-line loop body it
+The source orders  fragment loads + DMMAs -> fence.proxy.async (every lane) -> __syncwarp() -> arrive;
+the proxy fence (SASS `MEMBAR.ALL.CTA` + `FENCE.VIEW.ASYNC.S`) is the ordering construct.  Before it
+existed ptxas was free to move the arrive (no register dependency): in a straight-line loop body it
 placed the arrive between the last LDS and the DMMAs that consume them, and the kernel then produced
-run-to-run different cubes (profiles/r01_ring_release_race.txt).  In-order issue makes the arrive safe
-iff all DMMAs of the stage (which wait for their LDS operands at issue) precede it.  This script
-asserts exactly that for every contract_kernel instantiation:  last DMMA < WARPSYNC < arrive.
+run-to-run different cubes (profiles/r01_ring_release_race.txt).  This script is the second guard: for
+every contract_kernel instantiation it asserts
+    last LDS < FENCE.VIEW.ASYNC < WARPSYNC < arrive     and     last DMMA < arrive
+(the latter alone is what made the unfenced kernel safe: in-order issue, DMMAs wait for their LDS
+operands).
 
   python tools/check_sass_order.py [path/to/libatrip_b200.so]      exit code 1 on a violation
 """
@@ -32,11 +35,15 @@ def check(lib):
         dmma = [i for i, l in enumerate(ins) if "DMMA" in l]
         lds = [i for i, l in enumerate(ins) if re.search(r"\bLDS", l)]
         wsync = [i for i, l in enumerate(ins) if "WARPSYNC" in l]
+        fence = [i for i, l in enumerate(ins) if "FENCE.VIEW.ASYNC" in l]
         ok = len(arrive) == 1 and dmma and lds
         if ok:
             a = arrive[0]
             before = [w for w in wsync if w < a]
+            fbefore = [f for f in fence if max(lds) < f < a]
             ok = max(dmma) < a and max(lds) < a and bool(before) and max(before) > max(dmma) and max(before) > max(lds)
+            # the proxy fence sits between the last fragment load and the warp rendezvous
+            ok = ok and bool(fbefore) and min(fbefore) < max(before)
         if not ok:
             bad.append(name)
     return seen, bad
