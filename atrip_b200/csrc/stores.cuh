@@ -520,8 +520,8 @@ __global__ void upload_slices_kernel(int kind, const double *src, const long lon
 }
 
 // n slices of one kind back to the reference's slice layout (the inverse of the above); a slice
-// this rank does not hold comes back as NaN.  TABIJ(x,y) is read from the TA(x) rows (kind 201
-// therefore needs x owned), as read_slice_kernel does.
+// this rank does not hold comes back as NaN.  TABIJ(x,y) is read from the TA(x) rows when x is owned
+// (as read_slice_kernel does), else from the hole part of the (y,x)' slot held for y.
 template <bool Z>
 __global__ void read_slices_kernel(int kind, double *out, const long long *xy, int n, StoreDims d, SliceTables tb,
                                    const double *AX, const double *BY, const double *VIJ) {
@@ -533,7 +533,16 @@ __global__ void read_slices_kernel(int kind, double *out, const long long *xy, i
     const size_t s = g / per, e = g - s * per;
     const long long x = xy[2 * s], y = xy[2 * s + 1];
     double re = nan, im = nan;
-    if (kind == 100 || kind == 101 || kind == 201) {
+    if (kind == 201 && tb.xtab[x] < 0) {
+      // x is not owned here: the slice lives in the hole part of the (y,x)' slot this rank holds for y
+      const int s2 = tb.btab[x == y ? (long long)(Nv * Nv) + x : y + x * (long long)Nv];
+      if (s2 >= 0) {
+        const size_t p = e % No, q = e / No;
+        const double *row = BY + ((size_t)s2 * No + p) * Kp;
+        re = row[Nv + q];
+        if (Z) im = row[Kh + Nv + q];
+      }
+    } else if (kind == 100 || kind == 101 || kind == 201) {
       const int slot = tb.xtab[x];
       if (slot >= 0) {
         const double *A = AX + (size_t)slot * (Z ? 2 : 1) * No * No * Kp;  // variant 0 rows: [Re A | -Im A]

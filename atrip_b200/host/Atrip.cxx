@@ -4,7 +4,9 @@
 // tensors, slicing of the four big tensors, tuple distribution, checkpoint, progress callback,
 // max_iterations, energy reduction and sign -- while the per-tuple work, the slice stores and
 // the tuple schedule live on the device.
+#include <algorithm>
 #include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <fstream>
 #include <iomanip>
@@ -79,6 +81,65 @@ struct EngineHandle {
   }
 };
 
+// Several ranks: every rank slices, out of the (distributed) CTF tensor, only the sources it owns and
+// hands them to the engine one batch of slices at a time -- what SliceUnion<F>::init does with
+// slice_into_buffer / slice_into_vector (SliceUnion.cxx:305-332, Unions.hpp:21-75, 96-112, ...).
+// CTF::Tensor::slice is collective over the tensor's world, so every rank makes the same number of
+// slice calls: ranks with fewer sources repeat their first one, like the reference's source padding
+// (SliceUnion.cxx:322-326).  kind: atrip_b200_upload_slices; box(x, y, low, up) = the source box.
+template <typename F, typename Box>
+void upload_owned(atrip_b200_ctx *ctx, CTF::Tensor<F> *origin, int kind, std::vector<int> const &slice_lens, Box box) {
+  const int np = (int)Atrip::np, me = (int)Atrip::rank;
+  // (x, y) lists: mine, and the longest list of any rank (for the padding)
+  int64_t n_mine = 0, n_max = 0;
+  const int64_t nv = kind == 101 || kind == 111 ? origin->lens[3] : origin->lens[0];
+  std::vector<int64_t> xy;
+  for (int r = 0; r < np; r++) {
+    const int64_t n = atrip_b200_host_owned_slices(kind, nv, r, np, nullptr, 0);
+    if (n < 0) throw std::string("atrip_b200: owned_slices: ") + atrip_b200_last_error();
+    n_max = std::max(n_max, n);
+    if (r == me) n_mine = n;
+  }
+  xy.resize((size_t)std::max<int64_t>(1, 2 * n_mine));
+  atrip_b200_host_owned_slices(kind, nv, me, np, xy.data(), n_mine);
+  CTF::World self(MPI_COMM_SELF);
+  std::vector<int> syms(slice_lens.size(), NS), zero(slice_lens.size(), 0);
+  CTF::Tensor<F> to((int)slice_lens.size(), slice_lens.data(), syms.data(), self);
+  size_t per = 1;
+  for (int l : slice_lens) per *= (size_t)l;
+  // batches of up to ~32 MB of slices per engine call
+  const size_t per_call = std::max<size_t>(1, (size_t)(32u << 20) / (per * sizeof(F)));
+  std::vector<F> buf(per * std::min<size_t>(per_call, (size_t)std::max<int64_t>(1, n_mine)));
+  std::vector<int64_t> bxy;
+  size_t filled = 0;
+  auto flush = [&] {
+    if (!filled) return;
+    ok(atrip_b200_upload_slices(ctx, kind, (int64_t)filled, bxy.data(), reinterpret_cast<const double *>(buf.data())),
+       "upload_slices");
+    filled = 0;
+    bxy.clear();
+  };
+  for (int64_t it = 0; it < n_max; it++) {
+    const bool padding = it >= n_mine;
+    if (padding && n_mine == 0) {  // nothing owned at all: still take part in the collective slice
+      std::vector<int> low(origin->order, 0), up(origin->order, 1);
+      std::vector<int> tl(slice_lens.size(), 0), tu(slice_lens.size(), 1);
+      to.slice(tl.data(), tu.data(), F(0), *origin, low.data(), up.data(), F(1));
+      continue;
+    }
+    const int64_t x = xy[2 * (padding ? 0 : it)], y = xy[2 * (padding ? 0 : it) + 1];
+    std::vector<int> low, up;
+    box((int)x, (int)y, low, up);
+    to.slice(zero.data(), slice_lens.data(), F(0), *origin, low.data(), up.data(), F(1));
+    if (padding) continue;
+    std::copy(to.data, to.data + per, buf.begin() + filled * per);
+    bxy.push_back(x);
+    bxy.push_back(y);
+    if (++filled == per_call) flush();
+  }
+  flush();
+}
+
 // Atrip::run<F> for F = double and F = Complex: the engine computes both fields, the host logic is
 // the same (the reference's is one template, Atrip.cxx:65-1133)
 template <typename F>
@@ -137,27 +198,57 @@ Atrip::Output run_on_engine(Atrip::Input<F> const &in) {
       ok(atrip_b200_set_Tai(eng.ctx, tph.ptr), "set_Tai");
     }
     // the four big tensors -> HBM stores (replaces the five SliceUnion ctors, Atrip.cxx:277-332)
-    {
-      auto v = view(in.Vppph);
-      ok(atrip_b200_load_Vabci(eng.ctx, v.ptr), "load_Vabci");
-    }
-    if (in.delete_Vppph) delete in.Vppph;  // Atrip.cxx:310
-    {
-      auto v = view(in.Tpphh);
-      ok(atrip_b200_load_Tabij(eng.ctx, v.ptr), "load_Tabij");
-    }
-    {
-      auto v = view(in.Vpphh);
-      ok(atrip_b200_load_Vabij(eng.ctx, v.ptr), "load_Vabij");
-    }
-    {
-      auto v = view(in.Vhhhp);
-      ok(atrip_b200_load_Vijka(eng.ctx, v.ptr), "load_Vijka");
-    }
-    if (with_J) {
-      auto j1 = view(in.Jhhhp), j2 = view(in.Jppph);
-      ok(atrip_b200_load_Jijka(eng.ctx, j1.ptr), "load_Jijka");
-      ok(atrip_b200_load_Jabci(eng.ctx, j2.ptr), "load_Jabci");
+    const int iNo = (int)No, iNv = (int)Nv;
+    if (Atrip::np == 1) {
+      // one rank owns everything: stream the whole tensors through the engine's bulk ingest
+      {
+        auto v = view(in.Vppph);
+        ok(atrip_b200_load_Vabci(eng.ctx, v.ptr), "load_Vabci");
+      }
+      if (in.delete_Vppph) delete in.Vppph;  // Atrip.cxx:310
+      {
+        auto v = view(in.Tpphh);
+        ok(atrip_b200_load_Tabij(eng.ctx, v.ptr), "load_Tabij");
+      }
+      {
+        auto v = view(in.Vpphh);
+        ok(atrip_b200_load_Vabij(eng.ctx, v.ptr), "load_Vabij");
+      }
+      {
+        auto v = view(in.Vhhhp);
+        ok(atrip_b200_load_Vijka(eng.ctx, v.ptr), "load_Vijka");
+      }
+      if (with_J) {
+        auto j1 = view(in.Jhhhp), j2 = view(in.Jppph);
+        ok(atrip_b200_load_Jijka(eng.ctx, j1.ptr), "load_Jijka");
+        ok(atrip_b200_load_Jabci(eng.ctx, j2.ptr), "load_Jabci");
+      }
+    } else {
+      // several ranks: each slices and uploads only the sources it owns (SliceUnion.cxx:305-332); the
+      // boxes are the reference's (Unions.hpp:96-112 TAPHH, 134-151 HHHA, 177-196 ABPH, 219-236 ABHH,
+      // 258-277 TABHH)
+      auto ab_box = [&](int d2, int d3) {
+        return [=](int x, int y, std::vector<int> &low, std::vector<int> &up) {
+          low = {x, y, 0, 0};
+          up = {x + 1, y + 1, d2, d3};
+        };
+      };
+      auto hhha_box = [&](int x, int, std::vector<int> &low, std::vector<int> &up) {
+        low = {0, 0, 0, x};
+        up = {iNo, iNo, iNo, x + 1};
+      };
+      upload_owned<F>(eng.ctx, in.Vppph, 200, {iNv, iNo}, ab_box(iNv, iNo));  // ABPH
+      if (with_J) upload_owned<F>(eng.ctx, in.Jppph, 210, {iNv, iNo}, ab_box(iNv, iNo));
+      if (in.delete_Vppph) delete in.Vppph;  // Atrip.cxx:310
+      upload_owned<F>(eng.ctx, in.Tpphh, 100, {iNv, iNo, iNo},
+                      [&](int x, int, std::vector<int> &low, std::vector<int> &up) {  // TAPHH
+                        low = {x, 0, 0, 0};
+                        up = {x + 1, iNv, iNo, iNo};
+                      });
+      upload_owned<F>(eng.ctx, in.Tpphh, 201, {iNo, iNo}, ab_box(iNo, iNo));  // TABHH
+      upload_owned<F>(eng.ctx, in.Vpphh, 202, {iNo, iNo}, ab_box(iNo, iNo));  // ABHH
+      upload_owned<F>(eng.ctx, in.Vhhhp, 101, {iNo, iNo, iNo}, hhha_box);     // HHHA
+      if (with_J) upload_owned<F>(eng.ctx, in.Jhhhp, 111, {iNo, iNo, iNo}, hhha_box);
     }
     Atrip::chrono["slicing"] = t();
   }
@@ -172,21 +263,40 @@ Atrip::Output run_on_engine(Atrip::Input<F> const &in) {
   LOG(0, "Atrip") << "#iterations: " << n_iterations << "\n";
   const double doubles_flops = atrip_b200_flops_per_tuple(eng.ctx) / 1e9;  // GF per tuple, Atrip.cxx:578-580
 
-  // checkpoint (Atrip.cxx:586-621): resume at the stored iteration, rank 0 seeds its energy
+  if (in.rank_round_robin)
+    LOG(0, "Atrip") << "note: rank_round_robin has no effect, every GPU is its own node in the slice ownership map\n";
+  if (in.blocking)
+    LOG(0, "Atrip") << "note: blocking has no effect, slices are fetched one batch ahead on side streams\n";
+
+  // sum over the ranks: ncclAllReduce inside the engine (replaces MPI_Reduce, Atrip.cxx:1094-1107)
+  auto sum_ranks = [&](double *v, int n) {
+    if (Atrip::np > 1) ok(atrip_b200_allreduce(eng.ctx, v, n), "allreduce");
+  };
+
+  // checkpoint (Atrip.cxx:586-621): resume at the stored iteration, rank 0 seeds its energy.  The file
+  // stores ranks-per-node and nodes (Atrip.cxx:716-722); here every GPU is a node of its own.
   Output local{0, 0};
   size_t first_iteration = 0;
   const size_t checkpoint_mod = in.checkpoint_at_every_iteration != 0
                                     ? in.checkpoint_at_every_iteration
                                     : (size_t)(n_iterations * in.checkpoint_at_percentage / 100);
+  bool resumed = false;
   if (in.read_checkpoint_if_exists) {
     std::ifstream fin(in.checkpoint_path);
     if (fin.is_open()) {
       LOG(0, "Atrip") << "Reading checkpoint from " << in.checkpoint_path << "\n";
       const Checkpoint c = read_checkpoint(fin);
-      if (c.no != No || c.nv != Nv || c.iteration > n_iterations)
-        throw std::string("atrip: checkpoint ") + in.checkpoint_path + " does not belong to this calculation";
+      // the iteration counts tuples of THIS distribution over THIS many ranks: anything else is
+      // another calculation's file (the reference leaves these checks as TODOs, Atrip.cxx:599-610)
+      if (c.no != No || c.nv != Nv || c.iteration > n_iterations || c.nranks * c.nnodes != Atrip::np)
+        throw std::string("atrip: checkpoint ") + in.checkpoint_path +
+            " does not belong to this calculation (No, Nv, number of ranks or iteration differ)";
       first_iteration = c.iteration;
-      if (Atrip::rank == 0) local.energy = -c.energy;  // stored energy is the physical one
+      if (Atrip::rank == 0) {  // stored energies are the physical ones
+        local.energy = -c.energy;
+        local.ct_energy = c.has_ct ? -c.ct_energy : -c.energy;
+      }
+      resumed = true;
       LOG(0, "Atrip") << "iteration from checkpoint " << first_iteration << "\n";
     }
   }
@@ -200,14 +310,20 @@ Atrip::Output run_on_engine(Atrip::Input<F> const &in) {
   size_t report_mod = 0;
   if (in.percentage_mod > 0) report_mod = std::max<size_t>(1, n_iterations * (size_t)in.percentage_mod / 100);
   else if (in.iteration_mod > 0) report_mod = (size_t)in.iteration_mod;
-  size_t chunk = last > first_iteration ? last - first_iteration : 0;
-  if (report_mod) chunk = std::min(chunk, report_mod);
-  if (checkpoint_mod && in.writeCheckpoint) chunk = std::min(chunk, checkpoint_mod);
+  const size_t ckpt_mod = in.writeCheckpoint ? checkpoint_mod : 0;
+  // a device call runs up to the next report or checkpoint boundary (multiples of the two moduli)
+  auto next_boundary = [&](size_t it) {
+    size_t b = last;
+    if (report_mod) b = std::min(b, (it / report_mod + 1) * report_mod);
+    if (ckpt_mod) b = std::min(b, (it / ckpt_mod + 1) * ckpt_mod);
+    return b;
+  };
 
   Seconds loop;
   double device_ms = 0, tuples_done = 0;
+  bool wrote_checkpoint = false;
   for (size_t it = first_iteration; it < last;) {
-    const size_t n = std::min(chunk, last - it);
+    const size_t n = next_boundary(it) - it;
     double e = 0, ect = 0;
     ok(atrip_b200_run(eng.ctx, (int64_t)it, (int64_t)n, &e, &ect), "run");
     double tm[6];
@@ -223,24 +339,33 @@ Atrip::Output run_on_engine(Atrip::Input<F> const &in) {
       LOG(0, "Atrip") << "iteration " << it << " [" << 100 * it / std::max<size_t>(1, n_iterations) << "%] ("
                       << (device_ms > 0 ? doubles_flops * tuples_done / (device_ms * 1e-3) : -1) << "GF)\n";
     }
-    if (checkpoint_mod && in.writeCheckpoint && it < last && it % checkpoint_mod == 0) {
-      double global = 0;
-      MPI_Reduce(&local.energy, &global, 1, MPI_DOUBLE, MPI_SUM, 0, Atrip::communicator);
-      if (Atrip::rank == 0)
-        write_checkpoint({No, Nv, 1, Atrip::np, -global, it, in.rank_round_robin}, in.checkpoint_path);
+    if (ckpt_mod && it < last && it % ckpt_mod == 0) {
+      double g[2] = {local.energy, local.ct_energy};
+      sum_ranks(g, 2);
+      if (Atrip::rank == 0) {
+        Checkpoint c{No, Nv, 1, Atrip::np, -g[0], it, in.rank_round_robin};
+        c.ct_energy = -g[1];
+        c.has_ct = with_J;
+        write_checkpoint(c, in.checkpoint_path);
+      }
+      wrote_checkpoint = true;
     }
   }
   Atrip::chrono["iterations"] = loop();
   Atrip::chrono["device"] = device_ms * 1e-3;
 
   // energy reduction and sign (Atrip.cxx:1094-1111)
-  Output global{0, 0};
-  MPI_Reduce(&local.energy, &global.energy, 1, MPI_DOUBLE, MPI_SUM, 0, Atrip::communicator);
-  MPI_Reduce(&local.ct_energy, &global.ct_energy, 1, MPI_DOUBLE, MPI_SUM, 0, Atrip::communicator);
+  double g[2] = {local.energy, local.ct_energy};
+  sum_ranks(g, 2);
+  Output global{g[0], g[1]};
   if (!in.ijkabc) {
     global.energy = -global.energy;
     global.ct_energy = -global.ct_energy;
   }
+  // a run that walked the whole list is finished: its checkpoint must not survive, or the next run
+  // in this directory would resume from it and count most tuples twice
+  if (last == n_iterations && (wrote_checkpoint || resumed) && in.writeCheckpoint && Atrip::rank == 0)
+    std::remove(in.checkpoint_path.c_str());
   Atrip::chrono["total"] = total();
 
   // the reference leaves std::cout at 15 digits for its caller's "Energy:" line

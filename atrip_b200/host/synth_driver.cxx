@@ -1,9 +1,13 @@
 // Example/parity driver of the C++ API: builds CTF tensors holding the counter-based synthetic
 // inputs, calls atrip::Atrip::run<double> exactly like the reference's bench
 // (bench/main.cxx:345-391) and prints the energies in hex and decimal.
-//   synth_driver <No> <Nv> <seed> <scale> [max_iterations] [dist: group|naive] [cT|T] [complex]
+//   synth_driver <No> <Nv> <seed> <scale> [max_iterations] [dist: group|naive] [cT|T] [complex|real] [ijkabc]
 // With "complex" the tensors are CTF::Tensor<Complex> and atrip::Atrip::run<Complex> is called:
 // element e of a complex tensor is (synth(2e), synth(2e+1)), the epsilons are (synth(e), 0).
+// "ijkabc" sets Input::ijkabc (Atrip.cxx:183-187, 1108-1111).
+// Several ranks, one per GPU: start one process per rank with RANK / WORLD_SIZE / ATRIP_SHIM_MPI=1 and a
+// fresh ATRIP_SHIM_MPI_DIR in the environment (include/shim/mpi.h; tools/launch_ranks.py does it), or
+// build against a real MPI and use mpirun.  Rank 0 prints the RESULT line.
 #include <cinttypes>
 #include <cstdio>
 #include <cstdlib>
@@ -15,7 +19,7 @@
 static CTF::Tensor<double> *make(CTF::World &w, std::vector<int> lens, int tensor_id, uint64_t seed, double scale) {
   std::vector<int> syms(lens.size(), NS);
   auto *t = new CTF::Tensor<double>((int)lens.size(), lens.data(), syms.data(), w);
-  if (atrip_b200_synth_to_host(0, seed, tensor_id, scale, 0, (uint64_t)t->size, t->data) != 0) {
+  if (atrip_b200_synth_to_host(w.rank % std::max(1, atrip_b200_device_count()), seed, tensor_id, scale, 0, (uint64_t)t->size, t->data) != 0) {
     std::fprintf(stderr, "synth failed: %s\n", atrip_b200_last_error());
     std::exit(2);
   }
@@ -29,7 +33,7 @@ static CTF::Tensor<atrip::Complex> *make_z(CTF::World &w, std::vector<int> lens,
   double *d = reinterpret_cast<double *>(t->data);
   const uint64_t n = (uint64_t)t->size;
   const bool eps = tensor_id <= 1;
-  if (atrip_b200_synth_to_host(0, seed, tensor_id, scale, 0, eps ? n : 2 * n, d) != 0) {
+  if (atrip_b200_synth_to_host(w.rank % std::max(1, atrip_b200_device_count()), seed, tensor_id, scale, 0, eps ? n : 2 * n, d) != 0) {
     std::fprintf(stderr, "synth failed: %s\n", atrip_b200_last_error());
     std::exit(2);
   }
@@ -43,7 +47,7 @@ static CTF::Tensor<atrip::Complex> *make_z(CTF::World &w, std::vector<int> lens,
 
 template <typename F, typename Make>
 static int go(CTF::World &world, Make mk, int No, int Nv, uint64_t seed, double scale, size_t max_it, bool naive,
-              bool cT) {
+              bool cT, bool ijkabc) {
   using In = atrip::Atrip::Input<F>;
   auto in = In()
                 .with_epsilon_i(mk(world, {No}, 0, seed, scale))
@@ -58,6 +62,7 @@ static int go(CTF::World &world, Make mk, int No, int Nv, uint64_t seed, double 
                 .with_delete_Vppph(true)
                 .with_tuples_distribution(naive ? In::NAIVE : In::GROUP_AND_SORT)
                 .with_max_iterations(max_it)
+                .with_ijkabc(ijkabc)
                 .with_read_checkpoint_if_exists(false)
                 .with_writeCheckpoint(false)
                 .with_percentage_mod(25);
@@ -72,7 +77,8 @@ static int go(CTF::World &world, Make mk, int No, int Nv, uint64_t seed, double 
   }
   try {
     auto out = atrip::Atrip::run<F>(in);
-    std::printf("RESULT energy %a %.17g ct_energy %a %.17g\n", out.energy, out.energy, out.ct_energy, out.ct_energy);
+    if (world.rank == 0)
+      std::printf("RESULT energy %a %.17g ct_energy %a %.17g\n", out.energy, out.energy, out.ct_energy, out.ct_energy);
   } catch (std::string const &m) {
     std::printf("Atrip throwed with msg: %s\n", m.c_str());
     return 1;
@@ -82,7 +88,7 @@ static int go(CTF::World &world, Make mk, int No, int Nv, uint64_t seed, double 
 
 int main(int argc, char **argv) {
   if (argc < 5) {
-    std::fprintf(stderr, "usage: %s No Nv seed scale [max_iterations] [group|naive] [cT|T] [complex]\n", argv[0]);
+    std::fprintf(stderr, "usage: %s No Nv seed scale [max_iterations] [group|naive] [cT|T] [complex|real] [ijkabc]\n", argv[0]);
     return 2;
   }
   const int No = std::atoi(argv[1]), Nv = std::atoi(argv[2]);
@@ -95,8 +101,9 @@ int main(int argc, char **argv) {
   CTF::World world(argc, argv);
   atrip::Atrip::init(world.comm);
   const bool cplx = argc > 8 && !std::strcmp(argv[8], "complex");
-  const int rc = cplx ? go<atrip::Complex>(world, make_z, No, Nv, seed, scale, max_it, naive, cT)
-                      : go<double>(world, make, No, Nv, seed, scale, max_it, naive, cT);
+  const bool ijkabc = argc > 9 && !std::strcmp(argv[9], "ijkabc");
+  const int rc = cplx ? go<atrip::Complex>(world, make_z, No, Nv, seed, scale, max_it, naive, cT, ijkabc)
+                      : go<double>(world, make, No, Nv, seed, scale, max_it, naive, cT, ijkabc);
   if (rc) return rc;
   MPI_Finalize();
   return 0;

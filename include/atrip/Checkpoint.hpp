@@ -1,5 +1,7 @@
 // Checkpoint file of a (T) run: same "Key: value" text format as the reference
-// (src/atrip/Checkpoint.hpp:27-79), so files are interchangeable.
+// (src/atrip/Checkpoint.hpp:27-79), so files are interchangeable.  One optional extra key,
+// "CtEnergy", carries the (cT) partial sum (the reference's reader skips keys it does not know; its
+// checkpoint simply loses ct_energy on a resume).
 #pragma once
 #include <cstddef>
 #include <cstdlib>
@@ -14,6 +16,8 @@ struct Checkpoint {
   double energy = 0;
   size_t iteration = 0;
   bool rank_round_robin = false;
+  double ct_energy = 0;  // only written / valid when has_ct
+  bool has_ct = false;
 };
 
 inline void write_checkpoint(Checkpoint const &c, std::string const &path) {
@@ -21,6 +25,7 @@ inline void write_checkpoint(Checkpoint const &c, std::string const &path) {
   f << "No: " << c.no << "\nNv: " << c.nv << "\nNranks: " << c.nranks << "\nNnodes: " << c.nnodes
     << "\nEnergy: " << std::setprecision(19) << c.energy << "\nIteration: " << c.iteration
     << "\nRankRoundRobin: " << (c.rank_round_robin ? "true" : "false") << "\n";
+  if (c.has_ct) f << "CtEnergy: " << std::setprecision(19) << c.ct_energy << "\n";
 }
 
 inline Checkpoint read_checkpoint(std::ifstream &f) {
@@ -41,6 +46,10 @@ inline Checkpoint read_checkpoint(std::ifstream &f) {
     else if (key == "Energy") c.energy = std::strtod(val.c_str(), nullptr);
     else if (key == "Iteration") c.iteration = std::strtoull(val.c_str(), nullptr, 10);
     else if (key == "RankRoundRobin") c.rank_round_robin = !val.empty() && val[0] == 't';
+    else if (key == "CtEnergy") {
+      c.ct_energy = std::strtod(val.c_str(), nullptr);
+      c.has_ct = true;
+    }
   }
   return c;
 }

@@ -94,8 +94,7 @@ int atrip_b200_upload_slices(atrip_b200_ctx *ctx, int32_t kind, int64_t n, const
                              const double *host);
 int atrip_b200_upload_slice(atrip_b200_ctx *ctx, int32_t kind, int64_t x, int64_t y, const double *host);
 /*      the inverse, for parity tests and for building host-side shards: n slices of one kind back to the
- *      reference layout; a slice this rank does not hold comes back as NaN (kind 201 reads the TA(x) rows,
- *      so it needs x owned) */
+ *      reference layout; a slice this rank does not hold comes back as NaN */
 int atrip_b200_read_slices(atrip_b200_ctx *ctx, int32_t kind, int64_t n, const int64_t *xy, double *out);
 /*      host-only: the (x, y) list of the slices of `kind` rank `rank` of `nranks` has to be given; returns
  *      the count and writes at most cap pairs (xy may be NULL to query the count) */

@@ -323,6 +323,10 @@ class Reference:
             raise RuntimeError("reference threw: " + err.value.decode())
         return e.value, ct.value
 
+    def set_ijkabc(self, on):
+        """Input::ijkabc of the following run / run_z calls (needs an oracle/_ref built from this tree)"""
+        self.L.ref_set_ijkabc(int(bool(on)))
+
     def chrono(self, name):
         return self.L.ref_chrono(name.encode())
 

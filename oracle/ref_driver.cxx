@@ -27,7 +27,13 @@ CTF::Tensor<F> *wrap(CTF::World &w, std::vector<int> lens, const F *src) {
 bool initialised = false;
 } // namespace
 
+// Input::ijkabc of the following ref_run / ref_run_z calls (reference Atrip.cxx:183-187, 1108-1111:
+// Tai is negated and the final sign flip is skipped)
+static bool g_ijkabc = false;
+
 extern "C" {
+
+void ref_set_ijkabc(int on) { g_ijkabc = on != 0; }
 
 // atrip::Atrip::init + atrip::Atrip::run<double> (reference Atrip.cxx:54-63,
 // 65-1133) at np = 1 with GROUP_AND_SORT (the NAIVE distribution is broken at
@@ -66,6 +72,7 @@ int ref_run(int No, int Nv, const double *epsi, const double *epsa,
                   .with_Jijka(jhhhp)
                   .with_Jabci(jppph)
                   .with_delete_Vppph(false)
+                  .with_ijkabc(g_ijkabc)
                   .with_tuples_distribution(
                       Atrip::Input<double>::TuplesDistribution::GROUP_AND_SORT)
                   .with_max_iterations((size_t)max_iterations)
@@ -174,6 +181,7 @@ int ref_run_z(int No, int Nv, const double *epsi, const double *epsa,
                   .with_Jijka(jhhhp)
                   .with_Jabci(jppph)
                   .with_delete_Vppph(false)
+                  .with_ijkabc(g_ijkabc)
                   .with_tuples_distribution(
                       Atrip::Input<Complex>::TuplesDistribution::GROUP_AND_SORT)
                   .with_max_iterations((size_t)max_iterations)

@@ -74,3 +74,68 @@ def test_reference_bench_driver_runs_against_this_api():
     assert "Atrip throwed" not in out, out
     assert re.search(r"^Energy: ", out, re.M) and re.search(r"^Energy \(cT\): ", out, re.M), out
     assert "Progress(%)" in out  # the driver's register_iteration_descriptor callback fired
+
+
+def test_ijkabc_mode_matches_reference_vectors(driver):
+    """Input::ijkabc (Atrip.cxx:183-187: Tai negated; :1108-1111: no final sign flip), F = double and
+    F = Complex, against whole runs of the reference with the same switch (tests/golden/ijkabc_vectors.json)"""
+    import json
+    with open(os.path.join(ROOT, "tests", "golden", "ijkabc_vectors.json")) as f:
+        g = json.load(f)
+    for field, runs in (("real", g["runs"]), ("complex", g["complex_runs"])):
+        for r in runs:
+            cmd = [driver, str(r["No"]), str(r["Nv"]), str(r["seed"]), repr(r["scale"]), "0", "group",
+                   "cT" if r["with_J"] else "T", field, "ijkabc"]
+            rc, out = run(cmd)
+            assert rc == 0, out
+            e, ct = result(out)
+            ref, ref_ct = fh(r["energy"]), fh(r["ct_energy"])
+            assert ref > 0  # the unflipped sign
+            assert abs(e - ref) <= 1e-10 and abs(e - ref) <= 1e-12 * abs(ref), (field, r, e)
+            assert abs(ct - ref_ct) <= 1e-10 and abs(ct - ref_ct) <= 1e-11 * max(abs(ref), abs(ref_ct)), (field, r, ct)
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_atrip_run_on_several_ranks(driver, golden, world):
+    """one rank per GPU through the C++ API (reference Atrip.cxx:54-63, 84-91, 119): Atrip::init sees np
+    ranks (MPI stand-in in multi-process mode), every rank slices and uploads only the sources it owns
+    (SliceUnion.cxx:305-332), slices travel between the GPUs, the energy is summed by ncclAllReduce"""
+    import sys
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from launch_ranks import launch
+    for r in [golden["runs"][i] for i in (1, 3, 5)]:
+        cmd = [driver, str(r["No"]), str(r["Nv"]), str(r["seed"]), repr(r["scale"]), "0", "group",
+               "cT" if r["with_J"] else "T"]
+        rc, out, outs = launch(world, cmd)
+        assert rc == 0, outs
+        e, ct = result(out)
+        ref, ref_ct = fh(r["energy"]), fh(r["ct_energy"])
+        assert abs(e - ref) <= 1e-10 and abs(e - ref) <= 1e-12 * abs(ref), (r, e)
+        assert abs(ct - ref_ct) <= 1e-10 and abs(ct - ref_ct) <= 1e-11 * max(abs(ref), abs(ref_ct)), (r, ct)
+        assert f"np: {world}" in out
+    # complex field on two ranks
+    r = golden["complex_runs"][1]
+    rc, out, outs = launch(2, [driver, str(r["No"]), str(r["Nv"]), str(r["seed"]), repr(r["scale"]), "0", "group",
+                               "cT" if r["with_J"] else "T", "complex"])
+    assert rc == 0, outs
+    e, ct = result(out)
+    assert abs(e - fh(r["energy"])) <= 1e-12 * abs(e)
+
+
+def test_reference_bench_driver_on_two_ranks():
+    """the reference's own bench/main.cxx, unchanged, one process per GPU"""
+    import sys
+    import torch
+    exe = os.path.join(HOST, "atrip_bench")
+    if not os.path.exists(exe):
+        pytest.skip("atrip_bench is built only where /root/reference is present")
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from launch_ranks import launch
+    rc, out, outs = launch(2, [exe, "--no", "6", "--nv", "20", "--dist", "group", "--nocheckpoint", "-%", "50"], cwd="/tmp")
+    assert rc == 0, outs
+    assert "Atrip throwed" not in out and re.search(r"^Energy: ", out, re.M), out

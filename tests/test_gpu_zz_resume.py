@@ -42,3 +42,17 @@ def test_resume_from_checkpoint_reaches_the_uninterrupted_energy(field):
         resumed, out = drive(base + ["0"] + tail, env)
         assert "Reading checkpoint" in out and "iteration from checkpoint 40" in out
         assert abs(resumed - full) <= 1e-12 * abs(full), (resumed, full)
+        # a run that finished the list removes its checkpoint: the next run starts from scratch
+        assert not os.path.exists(ck)
+        again, out = drive(base + ["0"] + tail, env)
+        assert "Reading checkpoint" not in out and abs(again - full) <= 1e-12 * abs(full)
+
+
+def test_checkpoint_of_another_calculation_is_refused():
+    with tempfile.TemporaryDirectory() as tmp:
+        ck = os.path.join(tmp, "atrip-checkpoint.yaml")
+        open(ck, "w").write("No: 6\nNv: 15\nNranks: 1\nNnodes: 8\nEnergy: -0.5\nIteration: 40\nRankRoundRobin: false\n")
+        exe = os.path.join(HOST, "synth_driver")
+        p = subprocess.run([exe, "6", "15", "3", "0.05", "0", "group", "T"], capture_output=True, text=True, timeout=600,
+                           env=dict(os.environ, SYNTH_CHECKPOINT=ck))
+        assert p.returncode != 0 and "does not belong to this calculation" in p.stdout + p.stderr
