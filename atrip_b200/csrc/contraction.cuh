@@ -77,13 +77,19 @@ __host__ __device__ inline size_t contract_stage_bytes(int arows, int NI) {
   return (size_t)(arows + NI * 8) * 128;
 }
 
-template <int MI, int NI, int MAXT>
+// CREGS > 0: register re-allocation between the warp roles (setmaxnreg).  The block then carries a
+// whole producer warpgroup behind the consumer warps (warps nwarps .. nwarps+3, only the first one
+// works): it shrinks to 24 registers per thread and the consumer warpgroups grow to CREGS, beyond
+// the 65536 / MAXT cap of a uniform allocation (the register file is split per SM sub-partition: with
+// 8 consumer warps + 1 producer warp one sub-partition hosts 3 warps, which caps every thread at 168
+// registers and made the 4x8-fragment variant spill).  Needs nwarps % 4 == 0.
+template <int MI, int NI, int MAXT, int CREGS = 0>
 __global__ void __launch_bounds__(MAXT, 1)
 contract_kernel(const __grid_constant__ ContractMaps M, const ContractParams P) {
   extern __shared__ unsigned char smem_raw[];
   __shared__ uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES];
 
-  const int nwarps = (blockDim.x >> 5) - 1;
+  const int nwarps = (blockDim.x >> 5) - (CREGS ? 4 : 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   unsigned char *base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const size_t stage_bytes = contract_stage_bytes(P.arows, NI);
@@ -113,9 +119,10 @@ contract_kernel(const __grid_constant__ ContractMaps M, const ContractParams P) 
   int stage = 0;
   uint32_t phase = 0;
 
-  if (warp == nwarps) {
+  if (warp >= nwarps) {
     // ------------------------------------------------------------------ producer
-    if (lane == 0) {
+    if (CREGS) asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+    if (warp == nwarps && lane == 0) {
       const uint32_t tx = (uint32_t)((P.tu * P.tv + P.brows) * 128);
       for (long long item = blockIdx.x; item < nitems; item += gridDim.x) {
         const int tup = (int)(item / per_tuple);
@@ -152,6 +159,7 @@ contract_kernel(const __grid_constant__ ContractMaps M, const ContractParams P) 
   }
 
   // -------------------------------------------------------------------- consumers
+  if (CREGS) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(CREGS ? CREGS : 24));
   const int g = lane >> 2, t = lane & 3;
   const int perm = 2 * (g & 3) + (g >> 2);  // tile row (mod 8) held by fragment row g
   const uint32_t offA = (uint32_t)((warp * MI * 8 + perm) * 128 + (t & 1) * 8);

@@ -45,12 +45,18 @@ struct Fail {
 
 // ------------------------------------------------------------------ contraction kernel registry
 struct KernelVariant {
-  int MI, NI, maxt;
+  int MI, NI, maxt, cregs;
   const void *fn;
 };
-#define VARIANT(mi, ni, maxt) KernelVariant{mi, ni, maxt, (const void *)contract_kernel<mi, ni, maxt>}
-// accumulators take 4*MI*NI registers; the thread cap follows from the 64K register file
+#define VARIANT(mi, ni, maxt) KernelVariant{mi, ni, maxt, 0, (const void *)contract_kernel<mi, ni, maxt>}
+// 8 (or 4) consumer warps + a producer warpgroup, registers re-allocated between the roles with
+// setmaxnreg (contraction.cuh): 232 registers per consumer thread, no spills in any of them
+#define VARIANT_R(mi, ni) KernelVariant{mi, ni, 384, 232, (const void *)contract_kernel<mi, ni, 384, 232>}
+// accumulators take 4*MI*NI registers; the thread cap follows from the 64K register file (uniform
+// allocation: 16K registers per SM sub-partition, e.g. 3 warps of a 9-warp block on one of them -> 168)
 const KernelVariant kVariants[] = {
+    VARIANT_R(5, 5), VARIANT_R(4, 6), VARIANT_R(5, 6), VARIANT_R(4, 7), VARIANT_R(5, 7), VARIANT_R(4, 8),
+    VARIANT_R(5, 8), VARIANT_R(3, 10), VARIANT_R(4, 10), VARIANT_R(2, 13), VARIANT_R(3, 13),
     VARIANT(2, 1, 512), VARIANT(3, 1, 512), VARIANT(4, 1, 512), VARIANT(5, 1, 512),
     VARIANT(2, 2, 512), VARIANT(3, 2, 512), VARIANT(4, 2, 512), VARIANT(5, 2, 512),
     VARIANT(2, 3, 512), VARIANT(3, 3, 512), VARIANT(4, 3, 512), VARIANT(5, 3, 512),
@@ -79,9 +85,13 @@ struct ContractPlan {
 ContractPlan plan_contraction(int No, size_t smem_limit) {
   ContractPlan best;
   double best_score = -1;
+  const char *env = std::getenv("ATRIP_B200_NO_SETMAXNREG");  // developer knob: A/B against the uniform allocation
+  const bool no_r = env && std::atoi(env) != 0;
   for (const auto &k : kVariants) {
+    if (no_r && k.cregs) continue;
     const int ntiles = (No + k.NI * 8 - 1) / (k.NI * 8);
-    for (int nw = 4; nw <= k.maxt / 32 - 1; nw++) {
+    for (int nw = 4; nw <= k.maxt / 32 - (k.cregs ? 4 : 1); nw++) {
+      if (k.cregs && nw % 4) continue;  // setmaxnreg works on whole warpgroups
       const int arows = nw * k.MI * 8;
       const size_t stage = contract_stage_bytes(arows, k.NI);
       const int nstages = (int)std::min<size_t>(MAX_STAGES, (smem_limit - 2048) / stage);
@@ -254,6 +264,8 @@ struct atrip_b200_ctx {
   int last_nt = 0, last_buf = 0;  // tuples and cube buffer of the last batch run (debug checksum)
   bool reduce_async = false;      // ATRIP_B200_REDUCE=async: experimental bulk-copy reduction (reduction_async.cuh)
   bool reduce_reverse = false;    // ATRIP_B200_REDUCE=async-rev: ... walking the batch last tuple first
+  bool solo = false;              // ATRIP_B200_SOLO_SHARD=1 (profiling only): one rank of a sharded job runs alone, on
+                                  // tuples whose slices it owns itself (e.g. the c4 kernel shapes on one GPU)
 };
 
 namespace {
@@ -419,7 +431,7 @@ void launch_contract(atrip_b200_ctx *c, const TupleRec *d_recs, int ntuples, boo
   if (grid <= 0) return;
   ContractMaps *maps = useJ ? (avar ? &c->mapsJ1 : &c->mapsJ) : (avar ? &c->maps1 : &c->maps);
   void *args[2] = {(void *)maps, (void *)&P};
-  CUDA_OK(cudaLaunchKernel(contract_fn(c), dim3(grid), dim3((c->plan.nw + 1) * 32), args, c->plan.smem, c->stream));
+  CUDA_OK(cudaLaunchKernel(contract_fn(c), dim3(grid), dim3((c->plan.nw + (c->plan.k->cregs ? 4 : 1)) * 32), args, c->plan.smem, c->stream));
 }
 
 ReduceParams reduce_params(atrip_b200_ctx *c, const TupleRec *d_recs, int ntuples, bool ct, int buf) {
@@ -538,6 +550,7 @@ void create_impl(atrip_b200_ctx *c) {
                                (int)reduce_smem_bytes(c->No, false)));
   CUDA_OK(cudaFuncSetAttribute((const void *)reduce_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)reduce_smem_bytes(c->No, true)));
+  if (const char *e = std::getenv("ATRIP_B200_SOLO_SHARD")) c->solo = std::atoi(e) != 0;
   if (const char *e = std::getenv("ATRIP_B200_REDUCE")) {
     c->reduce_reverse = std::string(e) == "async-rev";
     c->reduce_async = (std::string(e) == "async" || c->reduce_reverse) && !c->cplx;
@@ -1044,7 +1057,7 @@ void exchange_step(atrip_b200_ctx *c, int64_t k, const BatchPlan *mine, const Ba
 
 // all ranks have finished filling their stores before anybody pulls from a peer
 void rank_barrier(atrip_b200_ctx *c) {
-  if (c->cfg.nranks == 1) return;
+  if (c->cfg.nranks == 1 || c->solo) return;
   REQUIRE(c->comm, "sharded stores need atrip_b200_comm_init before running tuples");
   CUDA_OK(cudaMemsetAsync(c->d_reduce, 0, sizeof(double), c->stream));
   NCCL_OK(nccl().AllReduce(c->d_reduce, c->d_reduce, 1, ncclFloat64, ncclSum, c->comm, c->stream));
@@ -1061,6 +1074,7 @@ void pull_step(atrip_b200_ctx *c, const BatchPlan *mine) {
   size_t ncopies = 0;
   for (const auto &v : mine->fetch) ncopies += v.size();
   if (!ncopies) return;
+  REQUIRE(!c->solo, "ATRIP_B200_SOLO_SHARD: a tuple reads a slice this rank does not own");
   const int ns = (int)std::min<size_t>(NXS, ncopies);
   if (ns > 1) {
     CUDA_OK(cudaEventRecord(c->xfork, c->xstream));
@@ -1099,8 +1113,8 @@ void run_list(atrip_b200_ctx *c, const Tuple *list, int64_t count, double *energ
               const Tuple *next = nullptr, int64_t next_count = 0) {
   const bool ct = c->have_J;
   const bool sh = sharded(c);
-  REQUIRE(!sh || c->comm, "sharded stores need atrip_b200_comm_init before running tuples");
-  REQUIRE(!sh || c->transport != 2 || !c->peer[0].empty(), "peer stores are not mapped");
+  REQUIRE(!sh || c->comm || c->solo, "sharded stores need atrip_b200_comm_init before running tuples");
+  REQUIRE(!sh || c->transport != 2 || !c->peer[0].empty() || c->solo, "peer stores are not mapped");
   const int64_t nb = (count + c->batch - 1) / c->batch;
   auto nt_of = [&](int64_t k) { return (size_t)std::min<int64_t>(c->batch, count - k * c->batch); };
   const bool p2p = sh && c->transport == 2;

@@ -39,11 +39,15 @@ def check(lib):
         ok = len(arrive) == 1 and dmma and lds
         if ok:
             a = arrive[0]
-            before = [w for w in wsync if w < a]
             fbefore = [f for f in fence if max(lds) < f < a]
-            ok = max(dmma) < a and max(lds) < a and bool(before) and max(before) > max(dmma) and max(before) > max(lds)
-            # the proxy fence sits between the last fragment load and the warp rendezvous
-            ok = ok and bool(fbefore) and min(fbefore) < max(before)
+            # the proxy fence sits between the last fragment load and the arrive ...
+            ok = max(dmma) < a and max(lds) < a and bool(fbefore)
+            # ... and in front of the warp rendezvous.  The setmaxnreg variants (template argument
+            # CREGS != 0) carry no WARPSYNC there: setmaxnreg.sync.aligned proves the warp converged, so
+            # ptxas drops the rendezvous -- all lanes issue every LDS / DMMA / arrive as one instruction.
+            between = [w for w in wsync if max(lds) < w < a]
+            converged = any("USETMAXREG" in l for l in ins)
+            ok = ok and (bool(between) or converged) and all(min(fbefore) < w for w in between)
         if not ok:
             bad.append(name)
     return seen, bad
