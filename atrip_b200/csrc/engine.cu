@@ -262,7 +262,7 @@ struct atrip_b200_ctx {
 
   double timing[16] = {0};
   int last_nt = 0, last_buf = 0;  // tuples and cube buffer of the last batch run (debug checksum)
-  bool reduce_async = false;      // ATRIP_B200_REDUCE=async: experimental bulk-copy reduction (reduction_async.cuh)
+  bool reduce_async = false;      // bulk-copy reduction kernel (reduction_async.cuh): default for the real field
   bool reduce_reverse = false;    // ATRIP_B200_REDUCE=async-rev: ... walking the batch last tuple first
   bool solo = false;              // ATRIP_B200_SOLO_SHARD=1 (profiling only): one rank of a sharded job runs alone, on
                                   // tuples whose slices it owns itself (e.g. the c4 kernel shapes on one GPU)
@@ -551,9 +551,13 @@ void create_impl(atrip_b200_ctx *c) {
   CUDA_OK(cudaFuncSetAttribute((const void *)reduce_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)reduce_smem_bytes(c->No, true)));
   if (const char *e = std::getenv("ATRIP_B200_SOLO_SHARD")) c->solo = std::atoi(e) != 0;
+  // reduction kernel of the (T) pass, real field: the bulk-copy kernel (reduction_async.cuh; measured r02c:
+  // 263 us vs 349 us per c2 launch).  ATRIP_B200_REDUCE=sync selects the register-staged kernel, =async-rev
+  // the bulk-copy kernel walking the batch last tuple first (developer A/B knobs)
+  c->reduce_async = !c->cplx;
   if (const char *e = std::getenv("ATRIP_B200_REDUCE")) {
-    c->reduce_reverse = std::string(e) == "async-rev";
-    c->reduce_async = (std::string(e) == "async" || c->reduce_reverse) && !c->cplx;
+    c->reduce_reverse = std::string(e) == "async-rev" && !c->cplx;
+    if (std::string(e) == "sync") c->reduce_async = false;
   }
   if (c->reduce_async)
     CUDA_OK(cudaFuncSetAttribute((const void *)reduce_async_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -139,3 +139,41 @@ def test_reference_bench_driver_on_two_ranks():
     rc, out, outs = launch(2, [exe, "--no", "6", "--nv", "20", "--dist", "group", "--nocheckpoint", "-%", "50"], cwd="/tmp")
     assert rc == 0, outs
     assert "Atrip throwed" not in out and re.search(r"^Energy: ", out, re.M), out
+
+
+def _write_tensor_files(oracle, tmp_path, r):
+    """the reference's on-disk tensor format (bench/main.cxx:54-75: CTF read_dense_from_file = raw native-endian
+    FP64 in global column-major order): the golden run's inputs, one file per tensor"""
+    from oracle.oracle import EPS_A, EPS_I, JABCI, JIJKA, TABIJ, TAI, VABCI, VABIJ, VIJKA
+    t = oracle.inputs(r["No"], r["Nv"], seed=r["seed"], scale=r["scale"], with_J=r["with_J"])
+    flags = {"--ei": EPS_I, "--ea": EPS_A, "--Tph": TAI, "--Tpphh": TABIJ, "--Vpphh": VABIJ, "--Vhhhp": VIJKA,
+             "--Vppph": VABCI}
+    if r["with_J"]:
+        flags.update({"--Jhhhp": JIJKA, "--Jppph": JABCI})
+    args = []
+    for flag, tid in flags.items():
+        path = os.path.join(str(tmp_path), flag.strip("-") + ".bin")
+        t[tid].astype("<f8").tofile(path)
+        args += [flag, path]
+    return args
+
+
+@pytest.mark.parametrize("idx", [5, 4])
+def test_reference_bench_driver_with_tensor_files(oracle, golden, tmp_path, idx):
+    """file inputs (survey row f3): the reference's unchanged bench/main.cxx reads every tensor with
+    read_dense_from_file (--ei --ea --Tph --Tpphh --Vpphh --Vhhhp --Vppph, --cT --Jhhhp --Jppph) and prints the
+    reference's own energies for those inputs (golden whole runs: No=10 Nv=40, and No=7 Nv=13 with J)"""
+    exe = os.path.join(HOST, "atrip_bench")
+    if not os.path.exists(exe):
+        pytest.skip("atrip_bench is built only where /root/reference is present")
+    r = golden["runs"][idx]
+    cmd = [exe, "--no", str(r["No"]), "--nv", str(r["Nv"]), "--dist", "group", "--nocheckpoint", "-%", "50"]
+    cmd += _write_tensor_files(oracle, tmp_path, r) + (["--cT"] if r["with_J"] else [])
+    rc, out = run(cmd, cwd=str(tmp_path))
+    assert rc == 0 and "Atrip throwed" not in out and "Random initialization" not in out, out
+    e = float(re.search(r"^Energy: (\S+)", out, re.M).group(1))
+    ct = float(re.search(r"^Energy \(cT\): (\S+)", out, re.M).group(1))
+    ref, ref_ct = fh(r["energy"]), fh(r["ct_energy"])
+    # the driver prints 15 significant digits (Atrip.cxx:1113-1116)
+    assert abs(e - ref) <= 2e-14 * abs(ref) + 1e-15, (e, ref)
+    assert abs(ct - ref_ct) <= 2e-14 * max(abs(ref), abs(ref_ct)) + 1e-15, (ct, ref_ct)

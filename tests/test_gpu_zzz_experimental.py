@@ -1,8 +1,8 @@
-"""GPU: opt-in experimental kernels against the default path.  These kernels were written when the
-round's GPU budget was already spent and have never run on a device: the tests are xfail(strict=False)
-so that the round-end GPU suite reports them (XPASS = works, xfail = needs work) without turning red,
-and every engine runs in a child process with a time limit, so that a kernel that hangs is killed
-with its CUDA context instead of stalling the suite."""
+"""GPU: the two reduction kernels against each other.  The default (T)-pass kernel of the real field is the
+bulk-copy kernel (reduction_async.cuh); ATRIP_B200_REDUCE=sync selects the register-staged kernel
+(reduction.cuh, still used for the (cT) pass), ATRIP_B200_REDUCE=async-rev the reversed tuple walk.  Every
+engine runs in a child process with a time limit, so that a kernel that hangs is killed with its CUDA
+context instead of stalling the suite."""
 import json
 import os
 import subprocess
@@ -41,13 +41,12 @@ def totals(No, Nv, reduce_mode):
     return np.array([float.fromhex(x) for x in json.loads(line[7:])])
 
 
-@pytest.mark.xfail(strict=False, reason="reduce_async_kernel (ATRIP_B200_REDUCE=async) has not run on a GPU yet")
-@pytest.mark.parametrize("mode", ["async", "async-rev"])
+@pytest.mark.parametrize("mode", ["sync", "async-rev"])
 @pytest.mark.parametrize("No,Nv", [(8, 16), (16, 24), (33, 40), (40, 56)])
-def test_async_reduction_matches_default(No, Nv, mode):
+def test_reduction_kernels_agree(No, Nv, mode):
     want = totals(No, Nv, None)
     try:
         got = totals(No, Nv, mode)
     except subprocess.TimeoutExpired:
-        pytest.fail("the experimental reduction did not finish within 120 s (killed)")
+        pytest.fail("the reduction did not finish within 120 s (killed)")
     assert np.all(np.abs(got - want) <= 1e-13 * np.abs(want)), (got, want)

@@ -12,6 +12,6 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
 # the two kernels, full set, third launch of each
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:contract_kernel -s 2 -c 1 \
     -f -o gpurun_out/${TAG}_contract $CMD > gpurun_out/${TAG}_contract.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:reduce_kernel -s 2 -c 1 \
+timeout 900 ncu --set full --clock-control none --import-source on -k 'regex:reduce_(async_)?kernel' -s 2 -c 1 \
     -f -o gpurun_out/${TAG}_reduce $CMD > gpurun_out/${TAG}_reduce.log 2>&1
 ls -la gpurun_out/${TAG}_*
