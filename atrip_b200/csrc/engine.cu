@@ -485,7 +485,7 @@ void launch_reduce(atrip_b200_ctx *c, const TupleRec *d_recs, int ntuples, bool 
     if (ct) reduce_z_kernel<true><<<grid, REDUCE_THREADS, smz, c->rstream>>>(P);
     else reduce_z_kernel<false><<<grid, REDUCE_THREADS, smz, c->rstream>>>(P);
   } else if (c->reduce_async && !ct) {
-    reduce_async_kernel<<<grid, REDUCE_THREADS, reduce_async_smem_bytes(c->No), c->rstream>>>(P);
+    reduce_async_kernel<<<grid, RA_THREADS, reduce_async_smem_bytes(c->No), c->rstream>>>(P);
   } else if (ct) reduce_kernel<true><<<grid, REDUCE_THREADS, smem, c->rstream>>>(P);
   else reduce_kernel<false><<<grid, REDUCE_THREADS, smem, c->rstream>>>(P);
   CUDA_OK(cudaGetLastError());

@@ -26,6 +26,7 @@ __device__ __forceinline__ void bulk_load_1d(void *dst, const void *src, uint32_
 }
 
 constexpr int RA_STAGE_DOUBLES = 18 * 512;  // 6 tiles x 3 classes x 4 KB
+constexpr int RA_THREADS = 256;              // 8 warps: 2 points of a tile per thread (ATRIP_B200_RA_THREADS at build time)
 
 __host__ __device__ inline size_t reduce_async_smem_bytes(int No) {
   return sizeof(double) * ((size_t)RA_STAGE_DOUBLES + 6 * RTILE + 18 * 64 + 4 * (size_t)No + 32) + 16;
@@ -51,7 +52,8 @@ struct OrbitWalk {
   __device__ void next() { skip(nsplit); }
 };
 
-__global__ void __launch_bounds__(REDUCE_THREADS, 2) reduce_async_kernel(const ReduceParams P) {
+__global__ void __launch_bounds__(RA_THREADS, 2) reduce_async_kernel(const ReduceParams P) {
+  constexpr int NQ = 512 / RA_THREADS;  // tile elements (and energy points) per thread
   extern __shared__ __align__(16) double sm_async[];
   double *St = sm_async;                              // [6 tiles][3 classes][512] raw class tiles of one orbit
   double *Wt = St + RA_STAGE_DOUBLES;           // [6][RTILE] summed, swizzled
@@ -77,7 +79,7 @@ __global__ void __launch_bounds__(REDUCE_THREADS, 2) reduce_async_kernel(const R
 #pragma unroll
   for (int q = 0; q < 3; q++)
     Vmat[q] = rec.vij[q] >= P.ownedV ? P.VIJc + (size_t)(rec.vij[q] - P.ownedV) * NoNo : P.VIJ + (size_t)rec.vij[q] * NoNo;
-  for (int i = tid; i < No; i += REDUCE_THREADS) {
+  for (int i = tid; i < No; i += RA_THREADS) {
     sEps[i] = P.eps_i[i];
     sTa[i] = P.Tai[a + (size_t)i * Nv];
     sTb[i] = P.Tai[b + (size_t)i * Nv];
@@ -120,10 +122,11 @@ __global__ void __launch_bounds__(REDUCE_THREADS, 2) reduce_async_kernel(const R
     }
   };
   // Vabij pair blocks of an orbit into registers (stored to Vb when the orbit becomes current)
-  auto load_v = [&](int I, int J, int K, double lv[9]) {
+  constexpr int NV = (18 * 64 + RA_THREADS - 1) / RA_THREADS;  // Vabij block elements per thread
+  auto load_v = [&](int I, int J, int K, double lv[NV]) {
 #pragma unroll
-    for (int q = 0; q < 9; q++) {
-      const int e = tid + REDUCE_THREADS * q;
+    for (int q = 0; q < NV; q++) {
+      const int e = min(tid + RA_THREADS * q, 18 * 64 - 1);
       const int mat = e / 384, r = e - mat * 384, pr = r >> 6, xl = r & 7, yl = (r >> 3) & 7;
       const int Xs = pr >> 1, Ys = (pr & 1) ? (Xs == 2 ? 1 : 2) : (Xs == 0 ? 1 : 0);
       const int x = pick3(Xs, I, J, K) * RT + xl, y = pick3(Ys, I, J, K) * RT + yl;
@@ -133,13 +136,14 @@ __global__ void __launch_bounds__(REDUCE_THREADS, 2) reduce_async_kernel(const R
   };
 
   OrbitWalk cur(nb, P.nsplit, split);
-  double lv[9];
+  double lv[NV];
   if (cur.valid) {
     if (tid == 0) issue(cur.I, cur.J, cur.K);
     load_v(cur.I, cur.J, cur.K, lv);
   }
   double esum = 0.0;
-  const int l0 = tid & 7, l1 = (tid >> 3) & 7, l2 = tid >> 6;
+  const int l0 = tid & 7, l1 = (tid >> 3) & 7, l2 = tid >> 6;  // l2 < RA_THREADS / 64; points (l0, l1, l2 + (8 / NQ) q)
+  constexpr int ZS = 8 / NQ;
   uint32_t phase = 0;
   while (cur.valid) {
     const int I = cur.I, J = cur.J, K = cur.K;
@@ -154,11 +158,13 @@ __global__ void __launch_bounds__(REDUCE_THREADS, 2) reduce_async_kernel(const R
       if (cm[p] != p) continue;
       const double *s = St + p * 3 * 512 + tid;
 #pragma unroll
-      for (int q = 0; q < 4; q++)
-        Wt[p * RTILE + tile_pos(l0, l1, l2 + 2 * q)] = (s[128 * q] + s[512 + 128 * q]) + s[1024 + 128 * q];
+      for (int q = 0; q < NQ; q++)
+        Wt[p * RTILE + tile_pos(l0, l1, l2 + ZS * q)] =
+            (s[RA_THREADS * q] + s[512 + RA_THREADS * q]) + s[1024 + RA_THREADS * q];
     }
 #pragma unroll
-    for (int q = 0; q < 9; q++) Vb[tid + REDUCE_THREADS * q] = lv[q];
+    for (int q = 0; q < NV; q++)
+      if (tid + RA_THREADS * q < 18 * 64) Vb[tid + RA_THREADS * q] = lv[q];
     __syncthreads();  // tiles and Vb published; staging free again
     // ---- next orbit: start its copies now, they fly during the energy phase below
     cur.next();
@@ -179,8 +185,8 @@ __global__ void __launch_bounds__(REDUCE_THREADS, 2) reduce_async_kernel(const R
       const double eij = sEps[i] + sEps[j];
       const double facij = (i == j) ? 0.5 : 1.0;
 #pragma unroll
-      for (int q = 0; q < 4; q++) {
-        const int kl = l2 + 2 * q, k = K * RT + kl;
+      for (int q = 0; q < NQ; q++) {
+        const int kl = l2 + ZS * q, k = K * RT + kl;
         if (k <= j) {
           const int o0 = tile_pos(il, jl, kl), o1 = RTILE * c1 + tile_pos(il, kl, jl);
           const int o2 = RTILE * c2 + tile_pos(jl, il, kl), o3 = RTILE * c3 + tile_pos(jl, kl, il);
@@ -223,7 +229,7 @@ __global__ void __launch_bounds__(REDUCE_THREADS, 2) reduce_async_kernel(const R
   __syncthreads();
   if (tid == 0) {
     double s = 0.0;
-    for (int w = 0; w < REDUCE_THREADS / 32; w++) s += sRed[w];
+    for (int w = 0; w < RA_THREADS / 32; w++) s += sRed[w];
     P.e_tuple[(size_t)tup * P.nsplit + split] = s;
   }
 }
