@@ -77,11 +77,11 @@ def pick_config(n_gpus):
         return "c3"
     try:
         import torch
-        total = torch.cuda.get_device_properties(0).total_memory
+        free, _total = torch.cuda.mem_get_info(int(os.environ.get("LOCAL_RANK", "0")))
     except Exception:
         return "c2"
-    # stores + 2 x 1 GiB of class cubes + ingest staging + CUDA context
-    return "c3" if total >= store_bytes(CONFIGS["c3"]) + 6 * 2 ** 30 else "c2"
+    # stores + 2 x 1 GiB of class cubes + ingest staging + CUDA context, against the memory that is free NOW
+    return "c3" if free >= store_bytes(CONFIGS["c3"]) + 5 * 2 ** 30 else "c2"
 
 
 # ----------------------------------------------------------------------------- clocks
@@ -382,6 +382,24 @@ def main():
     sharded = world > 1 and not args.replicate
     t_setup = time.perf_counter()
 
+    # N > 1: every GPU stores the slices it owns (RankMap round robin) and fetches the rest of each
+    # batch from its peers on side streams, one batch ahead of the compute
+    def make_engine(c):
+        return atrip_b200.Engine(c["No"], c["Nv"], device=local, rank=rank, nranks=world, resident=not sharded,
+                                 transport=args.transport,
+                                 field=capi.FIELD_COMPLEX if args.field == "complex" else capi.FIELD_REAL)
+    try:
+        eng = make_engine(cfg)
+    except capi.EngineError as e:
+        # c3 was picked from the GPU's total memory; if somebody else holds part of it, measure c2 instead
+        if args.config is not None or name != "c3" or world != 1:
+            raise
+        print(f"bench.py: c3 does not fit this GPU right now ({e}); falling back to c2", file=sys.stderr)
+        name = "c2"
+        cfg = dict(CONFIGS[name], name=name)
+        No, Nv, tps = cfg["No"], cfg["Nv"], cfg["tuples_per_step"]
+        eng = make_engine(cfg)
+
     # ------------------------------------------------ parity, part 1: host side starts now (rank 0)
     ptuples = parity_tuples(cfg)
     pq = pproc = None
@@ -395,11 +413,6 @@ def main():
         parity = {"n_gpus": world, "golden_run": golden_run_check(atrip_b200, capi, dist, rank, world, local, sharded,
                                                                   args.transport)}
 
-    # N > 1: every GPU stores the slices it owns (RankMap round robin) and fetches the rest of each
-    # batch from its peers on side streams, one batch ahead of the compute
-    eng = atrip_b200.Engine(No, Nv, device=local, rank=rank, nranks=world, resident=not sharded,
-                            transport=args.transport,
-                            field=capi.FIELD_COMPLEX if args.field == "complex" else capi.FIELD_REAL)
     if world > 1:  # the engine's own NCCL communicator; its 128-byte id travels over torch.distributed
         box = [capi.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(box, src=0)

@@ -1,6 +1,7 @@
 // Scalar helpers of the public API that the reference's driver uses
 // (reference src/atrip/Operations.hpp:28-53; bench/main.cxx:326-328).  Host-only here: the device
-// code of this build is FP64 real, for which conjugation is the identity.
+// code applies the conjugations of the complex field itself (stores.cuh: -conj(Vijka) in the AX
+// slices; reduction_z.cuh: conj(Tijk) in the energy sums).
 #pragma once
 #include <atrip/Complex.hpp>
 
