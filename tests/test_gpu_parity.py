@@ -239,3 +239,29 @@ def test_bench_size_tuples_vs_oracle(ab, oracle, No, Nv, tuples):
         assert np.abs(gZ - Z).max() <= CUBE_REL * np.abs(Z).max()
         assert abs(ge - e) <= E_REL * abs(e)
     eng.close()
+
+
+def test_two_live_engines_of_different_size(ab, golden):
+    """regression: the dynamic shared-memory cap is an attribute of the kernel FUNCTION, not of a context -- an
+    engine with a small No created while a larger one is alive used to lower the cap under it and the larger
+    engine's next reduction launch failed with "invalid argument" (bench.py keeps its engine while the golden
+    case runs).  Every combination of (T)/(cT) and both fields, interleaved."""
+    from atrip_b200 import capi
+    runs = {(r["No"], r["Nv"]): r for r in golden["runs"] if not r["with_J"]}
+    big_r, small_r = runs[(16, 24)], runs[(4, 8)]
+    big = ab.Engine(big_r["No"], big_r["Nv"], with_J=True)
+    big.fill_synthetic(big_r["seed"], big_r["scale"])
+    big.build_tuples(capi.GROUP_AND_SORT)
+    e0 = big.run()
+    small = ab.Engine(small_r["No"], small_r["Nv"], with_J=True)     # lowers nothing any more
+    small.fill_synthetic(small_r["seed"], small_r["scale"])
+    small.build_tuples(capi.GROUP_AND_SORT)
+    es = small.run()
+    small_z = ab.Engine(small_r["No"], small_r["Nv"], field=capi.FIELD_COMPLEX)
+    small_z.fill_synthetic(small_r["seed"], small_r["scale"])
+    small_z.build_tuples(capi.GROUP_AND_SORT)
+    small_z.run()
+    assert big.run() == e0                                           # the large engine still launches
+    assert close_energy(-e0[0], fh(big_r["energy"])) and close_energy(-es[0], fh(small_r["energy"]))
+    for e in (small_z, small, big):
+        e.close()
