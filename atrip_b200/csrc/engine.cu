@@ -1090,10 +1090,9 @@ void rank_barrier(atrip_b200_ctx *c) {
 // Two orderings, because the slots a copy overwrites were last addressed two batches earlier
 // (SliceCache): AX / BY slots are read by the contraction only, so their copies wait for
 // `after_contract` (contraction of that batch done); Vabij slots are read by the reduction only and
-// travel on their own stream c->xv behind `after_reduce`.  (One ordering behind the reduction made
-// every contraction wait for its fetch: the low-priority reduction of batch k-1 only gets SMs when
-// the contraction of batch k drains, so the copies of batch k+1 started exactly when the compute
-// stream wanted them -- 3.4 % of a c2 step on 2 GPUs, profiles/r02d_bench_c2_n2.json.)
+// travel on their own stream c->xv behind `after_reduce`.  (With one ordering behind the reduction the
+// copies of batch k+1 could only start when the low-priority reduction of batch k-1 had run, i.e. when
+// the contraction of batch k drained -- exactly when the compute stream wants them.)
 void pull_step(atrip_b200_ctx *c, const BatchPlan *mine, cudaEvent_t after_contract, cudaEvent_t after_reduce) {
   const bool J = c->have_J;
   if (after_contract) CUDA_OK(cudaStreamWaitEvent(c->xstream, after_contract, 0));

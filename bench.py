@@ -544,7 +544,7 @@ def main():
                                     "rank0_cache_hit_slices_per_step": hits / K,
                                     "rank0_fetched_slices_per_step": fetched / K,
                                     "rank0_host_plan_ms_per_step": plan_ms / K,
-                                    "rank0_fetch_wait_ms_per_step": gap_ms / K,
+                                    "rank0_idle_before_contraction_ms_per_step": gap_ms / K,  # fetch not landed OR cube buffer still being reduced
                                     "rank0_startup_gap_ms_per_step": start_ms / K,
                                     "max_rank_gap_fraction_of_step": gap_ms_max / dev_ms if dev_ms else None}},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches * world, "parity": parity,
