@@ -555,12 +555,15 @@ void create_impl(atrip_b200_ctx *c) {
   // while the golden case runs on a small one).  So every kernel gets the cap of the largest supported
   // problem (No = 256), not of this engine's No.
   const int kMaxNo = 256;
-  auto cap_of = [&](size_t bytes) { return (int)std::min(bytes, c->smem_limit); };
-  CUDA_OK(cudaFuncSetAttribute(contract_fn(c), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_limit));
-  CUDA_OK(cudaFuncSetAttribute((const void *)reduce_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               cap_of(reduce_smem_bytes(kMaxNo, false))));
-  CUDA_OK(cudaFuncSetAttribute((const void *)reduce_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               cap_of(reduce_smem_bytes(kMaxNo, true))));
+  auto set_cap = [&](const void *fn, size_t bytes) {  // dynamic cap <= opt-in limit - the kernel's static shared memory
+    cudaFuncAttributes fa;
+    CUDA_OK(cudaFuncGetAttributes(&fa, fn));
+    const size_t room = c->smem_limit - std::min(c->smem_limit, fa.sharedSizeBytes);
+    CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::min(bytes, room)));
+  };
+  set_cap(contract_fn(c), c->smem_limit);
+  set_cap((const void *)reduce_kernel<false>, reduce_smem_bytes(kMaxNo, false));
+  set_cap((const void *)reduce_kernel<true>, reduce_smem_bytes(kMaxNo, true));
   if (const char *e = std::getenv("ATRIP_B200_SOLO_SHARD")) c->solo = std::atoi(e) != 0;
   // reduction kernel of the (T) pass, real field: the bulk-copy kernel (reduction_async.cuh; measured r02c:
   // 263 us vs 349 us per c2 launch).  ATRIP_B200_REDUCE=sync selects the register-staged kernel, =async-rev
@@ -570,16 +573,13 @@ void create_impl(atrip_b200_ctx *c) {
     c->reduce_reverse = std::string(e) == "async-rev" && !c->cplx;
     if (std::string(e) == "sync") c->reduce_async = false;
   }
-  CUDA_OK(cudaFuncSetAttribute((const void *)reduce_async_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               cap_of(reduce_async_smem_bytes(kMaxNo))));
+  set_cap((const void *)reduce_async_kernel, reduce_async_smem_bytes(kMaxNo));
   REQUIRE(reduce_async_smem_bytes(c->No) <= c->smem_limit && reduce_smem_bytes(c->No, true) <= c->smem_limit,
           "No too large for the reduction kernels");
   if (c->cplx) {
     REQUIRE(reduce_z_smem_bytes(c->No, true) <= c->smem_limit, "No too large for the complex reduction kernel");
-    CUDA_OK(cudaFuncSetAttribute((const void *)reduce_z_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 cap_of(reduce_z_smem_bytes(kMaxNo, false))));
-    CUDA_OK(cudaFuncSetAttribute((const void *)reduce_z_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 cap_of(reduce_z_smem_bytes(kMaxNo, true))));
+    set_cap((const void *)reduce_z_kernel<false>, reduce_z_smem_bytes(kMaxNo, false));
+    set_cap((const void *)reduce_z_kernel<true>, reduce_z_smem_bytes(kMaxNo, true));
   }
 
   // ---- which slices live here: everything (replica) or the slices this rank owns
