@@ -10,9 +10,9 @@
 // current orbit from the summed tiles:
 //     wait(staging of orbit n) -> sum the three classes into the swizzled W tiles -> barrier
 //     -> issue the bulk copies of orbit n+1 into the (now free) staging area -> energy of orbit n.
-// No register staging, no spills, loads always in flight; 110 KB of shared memory, 2 CTAs per SM.
-// Measured (round 2, call c): 263 us per c2 launch (699 tuples, 1.10 GB -> 4.2 TB/s) against 349 us;
-// whole runs +2.1 % (c2), +1.5 % (c3), +1.6 % (c4 shapes).
+// No register staging, no spills, loads always in flight; 110 KB of shared memory, 2 CTAs of 256 threads per SM.
+// Measured (round 2): 236 us per c2 launch (699 tuples, 1.10 GB -> 4.7 TB/s, profiles/r02i_reduce_async_c2_ncu.txt)
+// against 349 us of reduce_kernel; whole runs +2.5 % (c2), +1.5 % (c3), +1.7 % (c4 shapes).
 #pragma once
 #include "reduction.cuh"
 
@@ -26,7 +26,8 @@ __device__ __forceinline__ void bulk_load_1d(void *dst, const void *src, uint32_
 }
 
 constexpr int RA_STAGE_DOUBLES = 18 * 512;  // 6 tiles x 3 classes x 4 KB
-constexpr int RA_THREADS = 256;              // 8 warps: 2 points of a tile per thread (ATRIP_B200_RA_THREADS at build time)
+constexpr int RA_THREADS = 256;              // 8 warps: 2 points of a tile per thread (128 and 256 both work; 256
+                                             // hides the shared-memory latency better: 4.2 -> 4.7 TB/s on c2)
 
 __host__ __device__ inline size_t reduce_async_smem_bytes(int No) {
   return sizeof(double) * ((size_t)RA_STAGE_DOUBLES + 6 * RTILE + 18 * 64 + 4 * (size_t)No + 32) + 16;

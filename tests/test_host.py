@@ -124,3 +124,30 @@ def test_contraction_plan_is_valid_for_every_No(lib):
         [(5, 5), (4, 8), (2, 13), (4, 4)]
     with pytest.raises(capi.EngineError):
         capi.host_plan(257)
+
+
+def test_sass_order_checker_flags_a_hoisted_release(tmp_path, monkeypatch):
+    """the checker itself: a synthetic listing with the arrive between the last LDS and the DMMAs that consume it
+    (the round-1 race) is reported, the correct order is accepted"""
+    import importlib.util
+    import subprocess as sp
+    spec = importlib.util.spec_from_file_location("check_sass_order", os.path.join(ROOT, "tools", "check_sass_order.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+
+    def listing(body):
+        lines = ["\t\tFunction : _ZN2ab15contract_kernelILi2ELi2ELi512ELi0EEEvNS_12ContractMapsENS_14ContractParamsE"]
+        for n, ins in enumerate(body):
+            lines.append(f"        /*{16 * n:04x}*/                   {ins} ;")
+        return "\n".join(lines) + "\n"
+
+    good = ["LDS.64 R2, [R0]", "DMMA.8x8x4 R4, R2, R2, R4", "MEMBAR.ALL.CTA", "FENCE.VIEW.ASYNC.S", "WARPSYNC.ALL",
+            "@!P0 SYNCS.ARRIVE.TRANS64.A1T0 RZ, [UR4], RZ"]
+    bad = ["LDS.64 R2, [R0]", "WARPSYNC.ALL", "@!P0 SYNCS.ARRIVE.TRANS64.A1T0 RZ, [UR4], RZ", "DMMA.8x8x4 R4, R2, R2, R4"]
+    unfenced = ["LDS.64 R2, [R0]", "DMMA.8x8x4 R4, R2, R2, R4", "WARPSYNC.ALL", "@!P0 SYNCS.ARRIVE.TRANS64.A1T0 RZ, [UR4], RZ"]
+    for body, nbad in ((good, 0), (bad, 1), (unfenced, 1)):
+        class R:
+            stdout = listing(body)
+        monkeypatch.setattr(sp, "run", lambda *a, **k: R)
+        seen, flagged = mod.check("unused.so")
+        assert seen == 1 and len(flagged) == nbad, (body, flagged)
