@@ -151,3 +151,39 @@ def test_sass_order_checker_flags_a_hoisted_release(tmp_path, monkeypatch):
         monkeypatch.setattr(sp, "run", lambda *a, **k: R)
         seen, flagged = mod.check("unused.so")
         assert seen == 1 and len(flagged) == nbad, (body, flagged)
+
+
+def test_c_abi_header_is_plain_c_and_links(lib, tmp_path):
+    """the boundary is a C ABI: include/atrip_b200.h compiles as C99 (no C++ constructs, no torch types) and a C
+    program linked against the library reaches the host-only entry points (no GPU: create must fail loudly)"""
+    import subprocess
+    src = tmp_path / "abi.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "atrip_b200.h"
+int main(void) {
+  atrip_b200_config cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.No = 4; cfg.Nv = 8; cfg.nranks = 1; cfg.resident = 1;
+  atrip_b200_ctx *ctx = 0;
+  int rc = atrip_b200_create(&ctx, &cfg);
+  int64_t plan[11];
+  int prc = atrip_b200_host_plan(40, 0, plan);
+  int64_t n = atrip_b200_host_tuples(1, 8, 0, 1, 1, 0, 0);
+  printf("version %s create %d (%s) plan %d %lld %lld tuples %lld owner %d\n", atrip_b200_version(), rc,
+         rc ? atrip_b200_last_error() : "ok", prc, (long long)plan[0], (long long)plan[1], (long long)n,
+         (int)atrip_b200_host_slice_owner(200, 5, 2, 8, 4));
+  if (ctx) atrip_b200_destroy(ctx);
+  return 0;
+}
+''')
+    exe = tmp_path / "abi"
+    libdir = os.path.join(ROOT, "atrip_b200", "csrc")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I" + os.path.join(ROOT, "include"),
+                           "-o", str(exe), str(src), "-L" + libdir, "-latrip_b200", "-Wl,-rpath," + libdir])
+    out = subprocess.check_output([str(exe)], text=True)
+    assert "version atrip_b200" in out and " plan 0 5 5 " in out and " tuples 112 " in out and out.strip().endswith("owner 1"), out
+    import torch
+    if not torch.cuda.is_available():
+        assert " create 1 (" in out and "no CPU fallback" in out, out
