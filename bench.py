@@ -182,6 +182,14 @@ def cpu_sample_tuples(cfg, n):
     return np.array(out[:n], dtype=np.int64)
 
 
+def host_cores():
+    """host threads this process may use (what `nproc` prints: the affinity mask, not the machine's total)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def est_cpu_tuples(cfg, cores, seconds):
     flops = 12.0 * cfg["No"] ** 3 * (cfg["No"] + cfg["Nv"])
     per_tuple = flops / 6.0e9  # ~6 GF/s/core measured for the reference dgemm path (BASELINE.md)
@@ -192,7 +200,7 @@ def run_reference_arm(args, cfg):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    cores = host_cores()
     flops_per_tuple = 12.0 * cfg["No"] ** 3 * (cfg["No"] + cfg["Nv"])
     per_step = est_cpu_tuples(cfg, cores, 6.0)
     tuples = cpu_sample_tuples(cfg, per_step * (args.steps + args.warmup))
@@ -507,7 +515,7 @@ def main():
     # ------------------------------------------------ CPU baseline beside it (rank 0, N=1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        cores = os.cpu_count() or 1
+        cores = host_cores()
         n = est_cpu_tuples(cfg, cores, args.cpu_seconds)
         tl = cpu_sample_tuples(cfg, n)
         with mp.get_context("spawn").Pool(cores) as pool:
