@@ -187,3 +187,26 @@ int main(void) {
     import torch
     if not torch.cuda.is_available():
         assert " create 1 (" in out and "no CPU fallback" in out, out
+
+
+@pytest.mark.parametrize("Nv,n", [(1, 1), (2, 1), (2, 4), (3, 8), (5, 8), (9, 2)])
+def test_tiny_and_ragged_tuple_lists(lib, Nv, n):
+    """edge cases of the distribution: fewer virtual orbitals than ranks, a single orbital (no tuple at all), lists
+    padded with FAKE_TUPLE to the longest rank's length; every tuple a<=b<=c (not all equal) appears exactly once"""
+    from atrip_b200 import capi
+    seen, lengths = set(), set()
+    for r in range(n):
+        tl = capi.host_tuples(capi.GROUP_AND_SORT, Nv, r, n, pad=True)
+        lengths.add(len(tl))
+        for a, b, c in tl[tl.any(axis=1)].tolist():
+            assert a <= b <= c < Nv and not (a == b == c) and (a, b, c) not in seen
+            seen.add((a, b, c))
+    assert len(lengths) == 1 and len(seen) == Nv * (Nv + 1) * (Nv + 2) // 6 - Nv
+
+
+def test_plan_rejects_unsupported_No(lib):
+    from atrip_b200 import capi
+    for bad in (0, 257, -3):
+        with pytest.raises(Exception):
+            capi.host_plan(bad)
+    assert capi.host_plan(256)["useful"] > 0.99 and capi.host_plan(1)["stages"] >= 3
