@@ -265,3 +265,28 @@ def test_two_live_engines_of_different_size(ab, golden):
     assert close_energy(-e0[0], fh(big_r["energy"])) and close_energy(-es[0], fh(small_r["energy"]))
     for e in (small_z, small, big):
         e.close()
+
+
+@pytest.mark.parametrize("No,Nv", [(1, 2), (1, 3), (2, 2), (3, 5), (2, 9), (9, 2), (17, 3)])
+def test_smallest_and_lopsided_problems(ab, oracle, No, Nv):
+    """edge cases: a single occupied orbital (every energy term vanishes at i=j=k), two virtual orbitals (only
+    "same" tuples), more occupied than virtual orbitals; (T) and (cT), real and complex field, against the oracle
+    (green on a B200: profiles/r02o_edge_cases_gpu.txt)"""
+    from atrip_b200 import capi
+    t = oracle.inputs(No, Nv, seed=5, scale=0.3, with_J=True)
+    want, want_ct = oracle.run(No, Nv, t)
+    eng = ab.Engine(No, Nv, with_J=True)
+    eng.fill_synthetic(5, 0.3)
+    eng.build_tuples(capi.GROUP_AND_SORT)
+    e, ct = eng.run()
+    eng.close()
+    assert abs(-e - want) <= E_REL * abs(want) + 1e-15, (-e, want)
+    assert abs(-ct - want_ct) <= 1e-11 * max(abs(want), abs(want_ct)) + 1e-15, (-ct, want_ct)
+    tz = oracle.inputs_z(No, Nv, seed=5, scale=0.3)
+    wz, _ = oracle.run_z(No, Nv, tz)
+    eng = ab.Engine(No, Nv, field=capi.FIELD_COMPLEX)
+    eng.fill_synthetic(5, 0.3)
+    eng.build_tuples(capi.GROUP_AND_SORT)
+    ez, _ = eng.run()
+    eng.close()
+    assert abs(-ez - wz) <= E_REL * abs(wz) + 1e-15, (-ez, wz)
