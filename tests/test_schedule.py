@@ -200,3 +200,21 @@ def test_owned_slice_lists_cover_every_slice_once_per_holder(lib):
                 assert seen[capi.TABIJ][(x, y)] == {x % n, y % n}
                 assert seen[capi.VABIJ][(x, y)] == {x % n, y % n}
     assert len(seen[capi.VABCI]) == Nv * Nv and len(seen[capi.TABIJ]) == Nv * (Nv + 1) // 2
+
+
+def test_tuples_distribution_dry_run_tool(lib):
+    """tools/tuples_distribution.py (the host-only analog of the reference's bench/tuples-distribution.cxx): whole
+    lists of every rank through the persistent-cache replay checker; the fetch counts are consistent"""
+    import os
+    import subprocess
+    import sys
+    from conftest import ROOT
+    out = subprocess.check_output([sys.executable, os.path.join(ROOT, "tools", "tuples_distribution.py"), "--no", "8",
+                                   "--nv", "24", "--ranks", "3", "--batch", "16", "--calls", "3"], text=True)
+    rows = [l.split() for l in out.splitlines() if l and l[0] == " " and l.split()[0].isdigit()]
+    assert len(rows) == 3, out
+    total = 0
+    for r in rows:
+        tuples, fakes = int(r[1]), int(r[2])
+        total += tuples - fakes
+    assert total == 24 * 25 * 26 // 6 - 24, out
